@@ -1,0 +1,158 @@
+/* ta_b200.h -- C ABI of the B200-native spectral frontend for track-analyser.
+ *
+ * The reference (cillianjoy/track-analyser) has no FFI of its own: its hot path is
+ * reached through module-level Python functions that delegate to librosa /
+ * pyloudnorm.  This header is the boundary a maintainer
+ * binds instead (ctypes stub: INTEGRATION.md).  Each entry point names the
+ * reference call sites (paths under /root/reference/src/track_analyser) whose
+ * arithmetic it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative TA_ERR_* code; the text of
+ *     the last error on the calling thread is ta_last_error().  No C++ exception
+ *     and no abort() crosses this boundary.
+ *   - all `float*`/`double*`/`int32_t*` data pointers are DEVICE pointers owned by
+ *     the caller (torch tensors in the shipped Python shim).  The library never
+ *     allocates or frees caller-visible memory; scratch is the caller-provided
+ *     workspace (ta_workspace_bytes).  Plan tables are owned by the plan.
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work
+ *     on it and returns.  `*_host` entry points take HOST buffers, do the copies
+ *     themselves and synchronise the stream before returning.
+ *   - ragged batches: track i has n_samples[i] samples per channel and
+ *     T_i = 1 + n_samples[i] / hop frames.  All (rows, T_i) matrices of track i
+ *     are row-major with row pitch ld_i = ta_frame_pitch(T_i) (T_i rounded up to
+ *     a multiple of 32 floats so that every row starts on a 128-byte line) and
+ *     are packed track after track: matrix of track i starts at element
+ *     rows * frame_pitch_prefix[i].  Per-frame series use the same pitch.
+ *   - there is NO CPU fallback: with no CUDA device every entry point that needs
+ *     one fails with TA_ERR_CUDA.
+ */
+#ifndef TA_B200_H
+#define TA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TA_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define TA_API __attribute__((visibility("default")))
+#else
+#define TA_API
+#endif
+
+#define TA_OK 0
+#define TA_ERR_INVALID (-1)   /* bad argument */
+#define TA_ERR_CUDA (-2)      /* CUDA runtime/driver error (text in ta_last_error) */
+#define TA_ERR_UNSUPPORTED (-3)
+#define TA_ERR_WORKSPACE (-4) /* workspace too small */
+
+typedef struct ta_plan ta_plan;
+
+TA_API int ta_abi_version(void);
+TA_API const char* ta_last_error(void);
+
+/* Immutable per-configuration state: FFT twiddles, periodic Hann window (computed
+ * in double), sparse Slaney mel filterbank, bin frequencies, K-weighting biquads.
+ * Replaces the table construction inside librosa.stft / librosa.filters.mel /
+ * pyloudnorm.Meter.__init__ reached from features.py:79, tempo.py:19,
+ * analysis/structure.py:48-59, analysis/loudness.py:60. */
+typedef struct ta_plan_desc {
+    int32_t device;        /* CUDA device ordinal */
+    int32_t sample_rate;   /* Hz */
+    int32_t n_fft;         /* 1024, 2048 or 4096 */
+    int32_t hop;           /* hop length in samples, multiple of 4 */
+    int32_t n_mels;        /* mel bands (0: no mel tables) */
+    int32_t n_chroma;      /* chroma bins (12) */
+    int32_t tempogram_win; /* tempogram window in frames (384) */
+    int32_t reserved;      /* must be 0 */
+    double fmin;           /* mel lower edge, Hz */
+    double fmax;           /* mel upper edge, Hz; <= 0 means sample_rate / 2 */
+    double roll_percent;   /* spectral roll-off fraction (0.85) */
+    double meter_block;    /* loudness gating block in seconds (0.4); a double because pyloudnorm's
+                              block bounds int(T_g*(j*step)*rate) are evaluated in Python floats */
+} ta_plan_desc;
+
+TA_API int ta_plan_create(const ta_plan_desc* desc, ta_plan** out);
+TA_API void ta_plan_destroy(ta_plan* plan);
+TA_API int ta_plan_n_bins(const ta_plan* plan);
+
+/* Copies plan tables to host for inspection/tests: which = 0 window (n_fft f32),
+ * 1 dense mel basis (n_mels * n_bins f32), 2 bin frequencies (n_bins f64),
+ * 3 biquad coefficients (12 f64: b0 b1 b2 a0 a1 a2 shelf, then high-pass). */
+TA_API int ta_plan_table(const ta_plan* plan, int which, void* host_out, size_t bytes);
+
+static inline int64_t ta_frame_count(int64_t n_samples, int32_t hop) { return 1 + n_samples / hop; }
+static inline int64_t ta_frame_pitch(int64_t n_frames) { return (n_frames + 31) & ~(int64_t)31; }
+
+/* Track batch (device PCM, host metadata). */
+typedef struct ta_batch {
+    int32_t n_tracks;
+    int32_t channels;          /* 1: mono rows; 2: planar L then R per track */
+    const float* pcm;          /* device base; channel c of track i at pcm + pcm_offset[i] + c*n_samples[i] */
+    const int64_t* pcm_offset; /* host [n_tracks], element offsets, multiples of 4 */
+    const int64_t* n_samples;  /* host [n_tracks] */
+} ta_batch;
+
+/* Outputs of the fused frontend.  Any pointer may be NULL to skip that output
+ * (the dependent stages still run if a later output needs them).  Sizes use
+ * P = sum_i ta_frame_pitch(T_i), B = n_fft/2+1, M = n_mels. */
+typedef struct ta_frontend_out {
+    float* magnitude;      /* [B * P]  |STFT| of the mono (mid) signal: structure.py:48-51, features.py:79-80 */
+    float* mel;            /* [M * P]  mel power spectrogram: structure.py:53-59, inside tempo.py:19 */
+    float* onset_env;      /* [P]      onset-strength envelope: tempo.py:16-24 */
+    double* autocorr;      /* [P]      librosa.autocorrelate(onset_env): tempo.py:38 (float64 like numpy 1.26) */
+    double* flux_linear;   /* [P]      onset_strength(S=mel) on linear power: structure.py:194-196 */
+    double* ltas;          /* [n_tracks * B] time-mean of magnitude: features.py:80 */
+    double* centroid;      /* [P]      spectral centroid, Hz: features.py:97-100 */
+    int32_t* rolloff_bin;  /* [P]      roll-off bin index k (frequency = k*sr/n_fft): features.py:116-123 */
+    double* band_energy;   /* [n_tracks * 2 * B] per-bin time sums of |mid|^2 then |side|^2: stereo.py:95-122 */
+    double* moments;       /* [n_tracks * 8] sum L, R, L^2, R^2, LR, mid^2, side^2, n: stereo.py:62-83, loudness.py:118 */
+    double* kw_blocks;     /* [n_tracks * kw_pitch] K-weighted gating-block mean squares z_j: loudness.py:60-61 */
+    double* lufs;          /* [n_tracks] gated integrated loudness: loudness.py:61 */
+    double* rms_momentary; /* [n_tracks * rms_pitch] mean-square of centred frames, 0.4 s window: loudness.py:57 */
+    double* rms_short;     /* [n_tracks * rms_pitch] same, 3.0 s window: loudness.py:56 */
+    int32_t kw_pitch;      /* capacity per track of kw_blocks */
+    int32_t rms_pitch;     /* capacity per track of rms_momentary / rms_short */
+} ta_frontend_out;
+
+TA_API size_t ta_workspace_bytes(const ta_plan* plan, const ta_batch* batch);
+
+/* Fused schedule K1..K7 for a batch of tracks; see DESIGN.md for the kernels. */
+TA_API int ta_frontend_run(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* --- single-stage entry points (each is also a step of ta_frontend_run) ------ */
+
+/* K1+K2+K7: fused frame + Hann + FFT + |X| (+ mel, LTAS, centroid, roll-off, band sums).
+ * Replaces librosa.stft / melspectrogram / spectral_centroid / spectral_rolloff at
+ * features.py:79,97,116; stereo.py:95-96; structure.py:48,53; harmony.py:254. */
+TA_API int ta_stft_features(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* K3: power_to_db (top_db 80 against the per-track max) + lag-1 diff + half-wave
+ * rectification + mean over mel + 3-frame left pad: librosa.onset.onset_strength
+ * at tempo.py:19.  mel_max_bits: per-track float bit pattern of max(mel). */
+TA_API int ta_onset_flux(const ta_plan* plan, const ta_batch* batch, const float* mel,
+                  const uint32_t* mel_max_bits, float* onset_env, double* flux_linear, void* stream);
+
+/* K4: full-length autocorrelation irfft(|rfft(x, n_pad)|^2)[:T] in float64:
+ * librosa.autocorrelate at tempo.py:38. */
+TA_API int ta_autocorrelate(const ta_plan* plan, const ta_batch* batch, const float* onset_env,
+                     double* autocorr, void* workspace, size_t workspace_bytes, void* stream);
+
+/* K5+K6: one pass over the PCM: K-weighting biquad cascade as a chunked linear
+ * recurrence scan (float64 state, float32 round trip between stages like
+ * scipy.signal.lfilter inside pyloudnorm), gating-block energies, BS.1770 gating,
+ * mid/side/LR moments and the centred RMS frames: loudness.py:30-61,118; stereo.py:62-83. */
+TA_API int ta_time_domain(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TA_B200_H */

@@ -1,0 +1,96 @@
+// Internal declarations shared by the translation units of libta_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/ta_b200.h"
+
+namespace ta {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define TA_CUDA(expr)                                                         \
+    do {                                                                      \
+        cudaError_t _e = (expr);                                              \
+        if (_e != cudaSuccess) return ::ta::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define TA_REQUIRE(cond, msg)                    \
+    do {                                         \
+        if (!(cond)) {                           \
+            ::ta::set_error(std::string(msg));   \
+            return TA_ERR_INVALID;               \
+        }                                        \
+    } while (0)
+
+// Device-side per-track descriptor (built from ta_batch into the workspace).
+struct TrackDesc {
+    const float* ch0;    // L (or mono)
+    const float* ch1;    // R (nullptr for mono)
+    int64_t n_samples;
+    int64_t pitch_off;   // sum of frame pitches of earlier tracks
+    int32_t n_frames;    // T
+    int32_t ld;          // frame pitch of this track
+    int32_t tile_begin;  // first global tile index (K1)
+    int32_t chunk_begin; // first global chunk index (K5)
+};
+
+struct Biquad {
+    double b0, b1, b2, a1, a2;
+};
+
+}  // namespace ta
+
+struct ta_plan {
+    ta_plan_desc desc;
+    int n_bins;
+    int sm_count;
+    // device tables
+    float2* d_tw1 = nullptr;    // [15 * n_fft/16]
+    float2* d_tw2 = nullptr;    // [16 * n_fft/256]
+    float* d_window = nullptr;  // [n_fft] periodic Hann (float32 of the float64 window)
+    double* d_freqs = nullptr;  // [n_bins]
+    int* d_mel_start = nullptr; // [n_mels]
+    int* d_mel_len = nullptr;   // [n_mels]
+    int* d_mel_woff = nullptr;  // [n_mels]
+    float* d_mel_w = nullptr;   // [nnz]
+    // host copies
+    std::vector<float> h_window;
+    std::vector<float> h_mel_dense;
+    std::vector<double> h_freqs;
+    ta::Biquad shelf, highpass;
+    // loudness framing
+    int kw_block;   // samples per gating block (0.4 s)
+    int kw_step;    // gcd-granule of block bounds
+    int rms_m_frame, rms_m_hop, rms_s_frame, rms_s_hop;
+};
+
+namespace ta {
+// stage launchers (defined in the .cu files)
+struct HostBatch {
+    int n_tracks = 0, channels = 0;
+    std::vector<TrackDesc> tracks;
+    int64_t total_pitch = 0;   // P
+    int64_t total_samples = 0;
+    int total_tiles = 0;
+    int total_chunks = 0;
+    int max_frames = 0;
+};
+int build_host_batch(const ta_plan* plan, const ta_batch* b, HostBatch& hb);
+
+// workspace carve-up
+struct Workspace {
+    TrackDesc* d_tracks;       // [n_tracks]
+    uint32_t* d_mel_max;       // [n_tracks]
+    double* d_granules;        // granule sums of the time-domain pass (three areas)
+    size_t gran_doubles;
+    double* d_fft;             // autocorrelation scratch (complex double) [..]
+    size_t fft_elems;
+    unsigned char* end;
+};
+size_t carve_workspace(const ta_plan* plan, const HostBatch& hb, void* base, Workspace& ws);
+}  // namespace ta

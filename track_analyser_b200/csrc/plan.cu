@@ -1,0 +1,443 @@
+// Plan construction (host-side tables computed in double), error plumbing, batch
+// descriptors, workspace carve-up and the fused schedule of the C ABI.
+#include <cmath>
+#include <cstring>
+#include <numeric>
+
+#include "common.cuh"
+
+namespace ta {
+
+static thread_local std::string g_last_error;
+
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    g_last_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " at " + file + ":" +
+                   std::to_string(line);
+    return TA_ERR_CUDA;
+}
+
+// stage launchers defined in the other translation units
+int run_stft_features(const ta_plan*, const HostBatch&, const Workspace&, const ta_frontend_out*, cudaStream_t);
+int run_onset_flux(const ta_plan*, const HostBatch&, const TrackDesc*, const float* mel, const uint32_t* mel_max,
+                   float* onset_env, double* flux_linear, cudaStream_t);
+int run_autocorrelate(const ta_plan*, const HostBatch&, const TrackDesc*, const float* env, double* out,
+                      double* scratch, size_t scratch_elems, cudaStream_t);
+size_t autocorr_scratch_elems(const HostBatch&);
+int run_time_domain(const ta_plan*, const HostBatch&, const Workspace&, const ta_frontend_out*, cudaStream_t);
+int stft_tile_frames(int n_fft);
+int time_chunk_samples(const ta_plan*, int64_t total_samples);
+
+// ---------------------------------------------------------------------------
+// Slaney mel scale exactly as librosa.filters.mel(htk=False, norm="slaney")
+// ---------------------------------------------------------------------------
+static double hz_to_mel(double f) {
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = std::log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = std::log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+static void build_mel(const ta_plan_desc& d, int n_bins, const std::vector<double>& fftfreqs,
+                      std::vector<float>& dense) {
+    const int M = d.n_mels;
+    const double fmax = d.fmax > 0 ? double(d.fmax) : double(d.sample_rate) / 2;
+    const double lo = hz_to_mel(double(d.fmin)), hi = hz_to_mel(fmax);
+    std::vector<double> mel_f(M + 2);
+    for (int i = 0; i < M + 2; ++i) {
+        // numpy.linspace: start + i*step with step = (stop-start)/(num-1); last point is stop exactly
+        const double step = (hi - lo) / double(M + 1);
+        const double m = (i == M + 1) ? hi : lo + i * step;
+        mel_f[i] = mel_to_hz(m);
+    }
+    dense.assign(size_t(M) * n_bins, 0.f);
+    for (int i = 0; i < M; ++i) {
+        const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+        const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+        for (int k = 0; k < n_bins; ++k) {
+            const double lower = -(mel_f[i] - fftfreqs[k]) / fd0;
+            const double upper = (mel_f[i + 2] - fftfreqs[k]) / fd1;
+            const double w = std::max(0.0, std::min(lower, upper));
+            // librosa stores float32 weights, then scales in place by the float64 enorm
+            dense[size_t(i) * n_bins + k] = float(double(float(w)) * enorm);
+        }
+    }
+}
+
+static void biquad_kweight(int rate, Biquad& shelf, Biquad& hp, double coefs[12]) {
+    const double PI = 3.14159265358979323846;
+    {
+        const double G = 4.0, Q = 1.0 / std::sqrt(2.0), fc = 1500.0;
+        const double A = std::pow(10.0, G / 40.0);
+        const double w0 = 2.0 * PI * (fc / rate);
+        const double alpha = std::sin(w0) / (2.0 * Q);
+        const double c = std::cos(w0), sA = std::sqrt(A);
+        const double b0 = A * ((A + 1) + (A - 1) * c + 2 * sA * alpha);
+        const double b1 = -2 * A * ((A - 1) + (A + 1) * c);
+        const double b2 = A * ((A + 1) + (A - 1) * c - 2 * sA * alpha);
+        const double a0 = (A + 1) - (A - 1) * c + 2 * sA * alpha;
+        const double a1 = 2 * ((A - 1) - (A + 1) * c);
+        const double a2 = (A + 1) - (A - 1) * c - 2 * sA * alpha;
+        shelf = {b0 / a0, b1 / a0, b2 / a0, a1 / a0, a2 / a0};
+        const double t[6] = {b0 / a0, b1 / a0, b2 / a0, a0 / a0, a1 / a0, a2 / a0};
+        std::memcpy(coefs, t, sizeof(t));
+    }
+    {
+        const double Q = 0.5, fc = 38.0;
+        const double w0 = 2.0 * PI * (fc / rate);
+        const double alpha = std::sin(w0) / (2.0 * Q);
+        const double c = std::cos(w0);
+        const double b0 = (1 + c) / 2, b1 = -(1 + c), b2 = (1 + c) / 2;
+        const double a0 = 1 + alpha, a1 = -2 * c, a2 = 1 - alpha;
+        hp = {b0 / a0, b1 / a0, b2 / a0, a1 / a0, a2 / a0};
+        const double t[6] = {b0 / a0, b1 / a0, b2 / a0, a0 / a0, a1 / a0, a2 / a0};
+        std::memcpy(coefs + 6, t, sizeof(t));
+    }
+}
+
+template <typename T>
+static int upload(T** dptr, const std::vector<T>& h) {
+    TA_CUDA(cudaMalloc(reinterpret_cast<void**>(dptr), std::max<size_t>(1, h.size()) * sizeof(T)));
+    if (!h.empty()) TA_CUDA(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return TA_OK;
+}
+
+static int plan_build(ta_plan* p) {
+    const ta_plan_desc& d = p->desc;
+    const int N = d.n_fft, M = N / 16, Q = N / 256;
+    const double PI = 3.14159265358979323846;
+    TA_CUDA(cudaSetDevice(d.device));
+    cudaDeviceProp prop;
+    TA_CUDA(cudaGetDeviceProperties(&prop, d.device));
+    p->sm_count = prop.multiProcessorCount;
+    p->n_bins = N / 2 + 1;
+
+    // twiddles, exact to float rounding (angle reduced with integer arithmetic first)
+    std::vector<float2> tw1(size_t(15) * M), tw2(size_t(16) * Q);
+    for (int k1 = 1; k1 < 16; ++k1)
+        for (int r = 0; r < M; ++r) {
+            const double a = -2.0 * PI * double((r * k1) % N) / N;
+            tw1[size_t(k1 - 1) * M + r] = make_float2(float(std::cos(a)), float(std::sin(a)));
+        }
+    for (int k2 = 0; k2 < 16; ++k2)
+        for (int n3 = 0; n3 < Q; ++n3) {
+            const double a = -2.0 * PI * double(n3 * k2) / M;
+            tw2[size_t(k2) * Q + n3] = make_float2(float(std::cos(a)), float(std::sin(a)));
+        }
+    // periodic Hann, scipy.signal.get_window("hann", N, fftbins=True): 0.5 - 0.5 cos(2 pi n / N)
+    p->h_window.resize(N);
+    for (int n = 0; n < N; ++n) p->h_window[n] = float(0.5 - 0.5 * std::cos(2.0 * PI * n / N));
+    // numpy.fft.rfftfreq(n, d=1/sr): arange(n//2+1) * (1.0 / (n * d))
+    p->h_freqs.resize(p->n_bins);
+    {
+        const double dd = 1.0 / double(d.sample_rate);
+        const double val = 1.0 / (double(N) * dd);
+        for (int k = 0; k < p->n_bins; ++k) p->h_freqs[k] = double(k) * val;
+    }
+    int rc;
+    if ((rc = upload(&p->d_tw1, tw1))) return rc;
+    if ((rc = upload(&p->d_tw2, tw2))) return rc;
+    if ((rc = upload(&p->d_window, p->h_window))) return rc;
+    if ((rc = upload(&p->d_freqs, p->h_freqs))) return rc;
+
+    if (d.n_mels > 0) {
+        build_mel(d, p->n_bins, p->h_freqs, p->h_mel_dense);
+        std::vector<int> start(d.n_mels), len(d.n_mels), woff(d.n_mels);
+        std::vector<float> w;
+        for (int m = 0; m < d.n_mels; ++m) {
+            int lo = p->n_bins, hi = -1;
+            for (int k = 0; k < p->n_bins; ++k)
+                if (p->h_mel_dense[size_t(m) * p->n_bins + k] != 0.f) {
+                    lo = std::min(lo, k);
+                    hi = std::max(hi, k);
+                }
+            start[m] = (hi < 0) ? 0 : lo;
+            len[m] = (hi < 0) ? 0 : hi - lo + 1;
+            woff[m] = int(w.size());
+            for (int k = 0; k < len[m]; ++k) w.push_back(p->h_mel_dense[size_t(m) * p->n_bins + start[m] + k]);
+        }
+        if ((rc = upload(&p->d_mel_start, start))) return rc;
+        if ((rc = upload(&p->d_mel_len, len))) return rc;
+        if ((rc = upload(&p->d_mel_woff, woff))) return rc;
+        if ((rc = upload(&p->d_mel_w, w))) return rc;
+    }
+
+    double coefs[12];
+    biquad_kweight(d.sample_rate, p->shelf, p->highpass, coefs);
+
+    // loudness framing (analysis/loudness.py:35-38 and pyloudnorm block bounds)
+    auto rms_frame = [&](double seconds) {
+        int fl = std::max(1024, int(std::nearbyint(double(d.sample_rate) * seconds)));
+        if (fl % 2) fl += 1;
+        return fl;
+    };
+    p->rms_m_frame = rms_frame(double(d.meter_block));
+    p->rms_m_hop = std::max(1, p->rms_m_frame / 2);
+    p->rms_s_frame = rms_frame(3.0);
+    p->rms_s_hop = std::max(1, p->rms_s_frame / 2);
+    return TA_OK;
+}
+
+// pyloudnorm block bounds, evaluated with the identical double expressions
+void kw_block_bounds(const ta_plan* plan, int64_t n_samples, std::vector<int64_t>& lo, std::vector<int64_t>& hi) {
+    const double T_g = double(plan->desc.meter_block), step = 0.25;
+    const double rate = double(plan->desc.sample_rate);
+    const double T = double(n_samples) / rate;
+    lo.clear();
+    hi.clear();
+    if (double(n_samples) < T_g * rate) return;
+    const long long nb = (long long)(std::nearbyint((T - T_g) / (T_g * step)) + 1);
+    for (long long j = 0; j < nb; ++j) {
+        lo.push_back((int64_t)(T_g * (double(j) * step) * rate));
+        hi.push_back((int64_t)(T_g * (double(j) * step + 1) * rate));
+    }
+}
+
+int build_host_batch(const ta_plan* plan, const ta_batch* b, HostBatch& hb) {
+    TA_REQUIRE(b && b->n_tracks > 0, "batch must hold at least one track");
+    TA_REQUIRE(b->channels == 1 || b->channels == 2, "channels must be 1 or 2");
+    TA_REQUIRE(b->pcm && b->pcm_offset && b->n_samples, "batch pointers must not be NULL");
+    const int hop = plan->desc.hop, TF = stft_tile_frames(plan->desc.n_fft);
+    hb.n_tracks = b->n_tracks;
+    hb.channels = b->channels;
+    hb.tracks.resize(b->n_tracks);
+    int64_t pitch = 0, samples = 0;
+    long long tiles = 0;
+    for (int i = 0; i < b->n_tracks; ++i) {
+        const int64_t ns = b->n_samples[i];
+        TA_REQUIRE(ns >= 0, "n_samples must be >= 0");
+        TA_REQUIRE(b->pcm_offset[i] % 4 == 0, "pcm_offset must be a multiple of 4 elements");
+        TrackDesc& t = hb.tracks[i];
+        t.ch0 = b->pcm + b->pcm_offset[i];
+        t.ch1 = (b->channels == 2) ? t.ch0 + ns : nullptr;
+        t.n_samples = ns;
+        const int64_t T = ta_frame_count(ns, hop);
+        TA_REQUIRE(T < (int64_t(1) << 30), "track too long");
+        t.n_frames = int(T);
+        t.ld = int(ta_frame_pitch(T));
+        t.pitch_off = pitch;
+        t.tile_begin = int(tiles);
+        t.chunk_begin = 0;  // filled by the time-domain stage
+        pitch += t.ld;
+        samples += ns;
+        tiles += (T + TF - 1) / TF;
+        hb.max_frames = std::max(hb.max_frames, t.n_frames);
+        TA_REQUIRE(tiles < (1ll << 31), "batch too large");
+    }
+    hb.total_pitch = pitch;
+    hb.total_samples = samples;
+    hb.total_tiles = int(tiles);
+    // time-domain chunks
+    const int cs = time_chunk_samples(plan, samples);
+    long long chunks = 0;
+    for (int i = 0; i < b->n_tracks; ++i) {
+        hb.tracks[i].chunk_begin = int(chunks);
+        chunks += (hb.tracks[i].n_samples + cs - 1) / cs;
+    }
+    TA_REQUIRE(chunks < (1ll << 31), "batch too large");
+    hb.total_chunks = int(chunks);
+    return TA_OK;
+}
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+size_t td_granule_doubles(const ta_plan* plan, const HostBatch& hb);
+
+size_t carve_workspace(const ta_plan* plan, const HostBatch& hb, void* base, Workspace& ws) {
+    unsigned char* p = reinterpret_cast<unsigned char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        unsigned char* r = p ? p + off : nullptr;
+        off = align_up(off + bytes, 256);
+        return r;
+    };
+    ws.d_tracks = reinterpret_cast<TrackDesc*>(take(sizeof(TrackDesc) * hb.n_tracks));
+    ws.d_mel_max = reinterpret_cast<uint32_t*>(take(sizeof(uint32_t) * hb.n_tracks));
+    // granule sums: K-weighted, momentary hop, short-term hop
+    ws.gran_doubles = td_granule_doubles(plan, hb);
+    ws.d_granules = reinterpret_cast<double*>(take(sizeof(double) * ws.gran_doubles));
+    ws.fft_elems = autocorr_scratch_elems(hb);
+    ws.d_fft = reinterpret_cast<double*>(take(sizeof(double) * ws.fft_elems));
+    ws.end = p ? p + off : nullptr;
+    return off;
+}
+
+}  // namespace ta
+
+using namespace ta;
+
+extern "C" {
+
+int ta_abi_version(void) { return TA_ABI_VERSION; }
+const char* ta_last_error(void) { return g_last_error.c_str(); }
+
+int ta_plan_create(const ta_plan_desc* desc, ta_plan** out) {
+    TA_REQUIRE(desc && out, "desc/out must not be NULL");
+    *out = nullptr;
+    TA_REQUIRE(desc->n_fft == 1024 || desc->n_fft == 2048 || desc->n_fft == 4096, "n_fft must be 1024, 2048 or 4096");
+    TA_REQUIRE(desc->hop > 0 && desc->hop % 4 == 0, "hop must be a positive multiple of 4");
+    TA_REQUIRE(desc->sample_rate > 0, "sample_rate must be positive");
+    TA_REQUIRE(desc->n_mels >= 0 && desc->n_mels <= 1024, "n_mels out of range");
+    TA_REQUIRE(desc->roll_percent > 0.0 && desc->roll_percent < 1.0, "roll_percent must be in (0,1)");
+    TA_REQUIRE(desc->meter_block > 0.0, "meter_block must be positive");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        set_error(std::string("no CUDA device available (no CPU fallback): ") + cudaGetErrorString(e));
+        return TA_ERR_CUDA;
+    }
+    TA_REQUIRE(desc->device >= 0 && desc->device < ndev, "device ordinal out of range");
+    ta_plan* p = new (std::nothrow) ta_plan();
+    TA_REQUIRE(p, "out of host memory");
+    p->desc = *desc;
+    int rc = plan_build(p);
+    if (rc != TA_OK) {
+        ta_plan_destroy(p);
+        return rc;
+    }
+    *out = p;
+    return TA_OK;
+}
+
+void ta_plan_destroy(ta_plan* p) {
+    if (!p) return;
+    cudaFree(p->d_tw1);
+    cudaFree(p->d_tw2);
+    cudaFree(p->d_window);
+    cudaFree(p->d_freqs);
+    cudaFree(p->d_mel_start);
+    cudaFree(p->d_mel_len);
+    cudaFree(p->d_mel_woff);
+    cudaFree(p->d_mel_w);
+    delete p;
+}
+
+int ta_plan_n_bins(const ta_plan* plan) { return plan ? plan->n_bins : TA_ERR_INVALID; }
+
+int ta_plan_table(const ta_plan* plan, int which, void* host_out, size_t bytes) {
+    TA_REQUIRE(plan && host_out, "plan/host_out must not be NULL");
+    const void* src = nullptr;
+    size_t need = 0;
+    double coefs[12];
+    switch (which) {
+        case 0: src = plan->h_window.data(); need = plan->h_window.size() * sizeof(float); break;
+        case 1: src = plan->h_mel_dense.data(); need = plan->h_mel_dense.size() * sizeof(float); break;
+        case 2: src = plan->h_freqs.data(); need = plan->h_freqs.size() * sizeof(double); break;
+        case 3: {
+            Biquad s, h;
+            biquad_kweight(plan->desc.sample_rate, s, h, coefs);
+            src = coefs;
+            need = sizeof(coefs);
+            break;
+        }
+        default: set_error("unknown table id"); return TA_ERR_INVALID;
+    }
+    TA_REQUIRE(bytes >= need, "host_out too small");
+    std::memcpy(host_out, src, need);
+    return TA_OK;
+}
+
+size_t ta_workspace_bytes(const ta_plan* plan, const ta_batch* batch) {
+    if (!plan || !batch) return 0;
+    HostBatch hb;
+    if (build_host_batch(plan, batch, hb) != TA_OK) return 0;
+    Workspace ws;
+    return carve_workspace(plan, hb, nullptr, ws);
+}
+
+static int prepare(const ta_plan* plan, const ta_batch* batch, void* workspace, size_t workspace_bytes,
+                   cudaStream_t stream, HostBatch& hb, Workspace& ws) {
+    TA_REQUIRE(plan, "plan must not be NULL");
+    int rc = build_host_batch(plan, batch, hb);
+    if (rc != TA_OK) return rc;
+    const size_t need = carve_workspace(plan, hb, workspace, ws);
+    if (!workspace || workspace_bytes < need) {
+        set_error("workspace too small: need " + std::to_string(need) + " bytes");
+        return TA_ERR_WORKSPACE;
+    }
+    TA_CUDA(cudaSetDevice(plan->desc.device));
+    // descriptor upload: stream-ordered copy from a pageable host vector is staged by the runtime
+    TA_CUDA(cudaMemcpyAsync(ws.d_tracks, hb.tracks.data(), sizeof(TrackDesc) * hb.n_tracks, cudaMemcpyHostToDevice, stream));
+    return TA_OK;
+}
+
+int ta_stft_features(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+    TA_REQUIRE(out, "out must not be NULL");
+    HostBatch hb;
+    Workspace ws;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = prepare(plan, batch, workspace, workspace_bytes, st, hb, ws);
+    if (rc != TA_OK) return rc;
+    return run_stft_features(plan, hb, ws, out, st);
+}
+
+int ta_onset_flux(const ta_plan* plan, const ta_batch* batch, const float* mel, const uint32_t* mel_max_bits,
+                  float* onset_env, double* flux_linear, void* stream) {
+    TA_REQUIRE(plan && mel && mel_max_bits, "plan/mel/mel_max_bits must not be NULL");
+    HostBatch hb;
+    int rc = build_host_batch(plan, batch, hb);
+    if (rc != TA_OK) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TA_CUDA(cudaSetDevice(plan->desc.device));
+    // this stand-alone entry point has no workspace: descriptors travel through a stream-ordered allocation
+    TrackDesc* d_tracks = nullptr;
+    TA_CUDA(cudaMallocAsync(reinterpret_cast<void**>(&d_tracks), sizeof(TrackDesc) * hb.n_tracks, st));
+    TA_CUDA(cudaMemcpyAsync(d_tracks, hb.tracks.data(), sizeof(TrackDesc) * hb.n_tracks, cudaMemcpyHostToDevice, st));
+    rc = run_onset_flux(plan, hb, d_tracks, mel, mel_max_bits, onset_env, flux_linear, st);
+    cudaFreeAsync(d_tracks, st);
+    return rc;
+}
+
+int ta_autocorrelate(const ta_plan* plan, const ta_batch* batch, const float* onset_env, double* autocorr,
+                     void* workspace, size_t workspace_bytes, void* stream) {
+    TA_REQUIRE(onset_env && autocorr, "onset_env/autocorr must not be NULL");
+    HostBatch hb;
+    Workspace ws;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = prepare(plan, batch, workspace, workspace_bytes, st, hb, ws);
+    if (rc != TA_OK) return rc;
+    return run_autocorrelate(plan, hb, ws.d_tracks, onset_env, autocorr, ws.d_fft, ws.fft_elems, st);
+}
+
+int ta_time_domain(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out, void* workspace,
+                   size_t workspace_bytes, void* stream) {
+    TA_REQUIRE(out, "out must not be NULL");
+    HostBatch hb;
+    Workspace ws;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = prepare(plan, batch, workspace, workspace_bytes, st, hb, ws);
+    if (rc != TA_OK) return rc;
+    return run_time_domain(plan, hb, ws, out, st);
+}
+
+int ta_frontend_run(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    TA_REQUIRE(out, "out must not be NULL");
+    HostBatch hb;
+    Workspace ws;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = prepare(plan, batch, workspace, workspace_bytes, st, hb, ws);
+    if (rc != TA_OK) return rc;
+    const bool need_flux = out->onset_env || out->flux_linear || out->autocorr;
+    TA_REQUIRE(!need_flux || out->mel, "onset/autocorr outputs need the mel output buffer");
+    TA_REQUIRE(!out->autocorr || out->onset_env, "autocorr output needs the onset_env output buffer");
+    const bool need_stft = out->magnitude || out->mel || out->ltas || out->centroid || out->rolloff_bin || out->band_energy;
+    if (need_stft && (rc = run_stft_features(plan, hb, ws, out, st)) != TA_OK) return rc;
+    if (need_flux && (rc = run_onset_flux(plan, hb, ws.d_tracks, out->mel, ws.d_mel_max, out->onset_env,
+                                          out->flux_linear, st)) != TA_OK)
+        return rc;
+    if (out->autocorr &&
+        (rc = run_autocorrelate(plan, hb, ws.d_tracks, out->onset_env, out->autocorr, ws.d_fft, ws.fft_elems, st)) != TA_OK)
+        return rc;
+    const bool need_td = out->moments || out->kw_blocks || out->lufs || out->rms_momentary || out->rms_short;
+    if (need_td && (rc = run_time_domain(plan, hb, ws, out, st)) != TA_OK) return rc;
+    return TA_OK;
+}
+
+}  // extern "C"

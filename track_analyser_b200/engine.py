@@ -1,0 +1,245 @@
+"""Device-side driver: plans, batch packing and the fused frontend call.
+
+PyTorch is used only for memory ownership (pinned host staging, device buffers)
+and for the current CUDA stream; every number is produced by the kernels in
+``csrc/`` through the C ABI (``include/ta_b200.h``).  Tracks are independent
+(reference: pipeline.py:32 takes one source), so a batch is a ragged list of
+planar float32 arrays processed by one launch sequence.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Iterable, Sequence
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+ALL_OUTPUTS = (
+    "magnitude", "mel", "onset_env", "autocorr", "flux_linear", "ltas", "centroid", "rolloff_bin",
+    "band_energy", "moments", "kw_blocks", "lufs", "rms_momentary", "rms_short",
+)
+DEFAULT_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o != "magnitude")
+
+
+def frame_count(n_samples: int, hop: int) -> int:
+    return 1 + n_samples // hop
+
+
+def frame_pitch(n_frames: int) -> int:
+    return (n_frames + 31) & ~31
+
+
+@dataclass
+class TrackResult:
+    """Per-track host copies of the frontend outputs (numpy, reference shapes)."""
+
+    n_samples: int
+    n_frames: int
+    data: dict = field(default_factory=dict)
+
+    def __getitem__(self, key):
+        return self.data[key]
+
+    def __contains__(self, key):
+        return key in self.data
+
+
+class Plan:
+    """Owns a ``ta_plan`` (twiddles, window, mel filterbank, biquads) on one device."""
+
+    def __init__(self, sample_rate: int, n_fft: int = 2048, hop: int = 512, n_mels: int = 128,
+                 device: int | None = None, fmin: float = 0.0, fmax: float | None = None,
+                 roll_percent: float = 0.85, meter_block: float = 0.4, n_chroma: int = 12,
+                 tempogram_win: int = 384):
+        if not torch.cuda.is_available():
+            raise RuntimeError("track_analyser_b200 needs a CUDA device (B200); there is no CPU fallback")
+        self.lib = nat.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.sample_rate, self.n_fft, self.hop, self.n_mels = int(sample_rate), int(n_fft), int(hop), int(n_mels)
+        self.roll_percent, self.meter_block = float(roll_percent), float(meter_block)
+        desc = nat.PlanDesc(self.device, self.sample_rate, self.n_fft, self.hop, self.n_mels, int(n_chroma),
+                            int(tempogram_win), 0, float(fmin), float(fmax) if fmax else 0.0,
+                            self.roll_percent, self.meter_block)
+        handle = C.c_void_p()
+        nat.check(self.lib.ta_plan_create(C.byref(desc), C.byref(handle)))
+        self._h = handle
+        self.n_bins = self.n_fft // 2 + 1
+        self._ws = None  # cached workspace tensor
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.ta_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover - best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- tables (tests) -------------------------------------------------------
+    def table(self, which: str) -> np.ndarray:
+        spec = {"window": (0, np.float32, (self.n_fft,)), "mel": (1, np.float32, (self.n_mels, self.n_bins)),
+                "freqs": (2, np.float64, (self.n_bins,)), "biquads": (3, np.float64, (2, 6))}[which]
+        out = np.empty(spec[2], dtype=spec[1])
+        nat.check(self.lib.ta_plan_table(self._h, spec[0], out.ctypes.data_as(C.c_void_p), out.nbytes))
+        return out
+
+    # ---- loudness framing helpers ---------------------------------------------------
+    def rms_frames(self, seconds: float) -> tuple[int, int]:
+        frame = max(1024, int(round(self.sample_rate * seconds)))
+        if frame % 2:
+            frame += 1
+        return frame, max(1, frame // 2)
+
+    def kw_block_count(self, n_samples: int) -> int:
+        T_g = self.meter_block
+        if n_samples < T_g * self.sample_rate:
+            return 0
+        return int(np.round(((n_samples / self.sample_rate - T_g) / (T_g * 0.25))) + 1)
+
+
+class DeviceBatch:
+    """A ragged batch of tracks resident in HBM plus its host metadata."""
+
+    def __init__(self, plan: Plan, pcm: torch.Tensor, offsets: np.ndarray, n_samples: np.ndarray, channels: int):
+        self.plan, self.pcm, self.channels = plan, pcm, channels
+        self.offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        self.n_samples = np.ascontiguousarray(n_samples, dtype=np.int64)
+        self.n_tracks = len(self.n_samples)
+        self.n_frames = 1 + self.n_samples // plan.hop
+        self.pitch = (self.n_frames + 31) & ~31
+        self.pitch_off = np.concatenate([[0], np.cumsum(self.pitch)]).astype(np.int64)
+        self.total_pitch = int(self.pitch_off[-1])
+        self.c_batch = nat.Batch(self.n_tracks, channels, pcm.data_ptr(),
+                                 self.offsets.ctypes.data_as(C.POINTER(C.c_int64)),
+                                 self.n_samples.ctypes.data_as(C.POINTER(C.c_int64)))
+
+
+def pack_host(tracks: Sequence[np.ndarray], channels: int, pinned: bool = True):
+    """Pack float32 tracks ((C, N) planar or (N,)) into one flat host tensor; offsets are 4-aligned."""
+    n_samples, offsets, total = [], [], 0
+    for t in tracks:
+        n = t.shape[-1]
+        n_samples.append(n)
+        offsets.append(total)
+        total += (channels * n + 3) & ~3
+    host = torch.empty(max(total, 4), dtype=torch.float32, pin_memory=pinned)
+    hv = host.numpy()
+    for t, off, n in zip(tracks, offsets, n_samples):
+        hv[off: off + channels * n] = np.ascontiguousarray(t, dtype=np.float32).reshape(-1)
+    return host, np.asarray(offsets, dtype=np.int64), np.asarray(n_samples, dtype=np.int64)
+
+
+def upload(plan: Plan, tracks: Sequence[np.ndarray]) -> DeviceBatch:
+    tracks = [np.asarray(t, dtype=np.float32) for t in tracks]
+    chans = {1 if t.ndim == 1 else t.shape[0] for t in tracks}
+    if len(chans) != 1 or next(iter(chans)) not in (1, 2):
+        raise ValueError("a batch must hold tracks that are all mono (N,) / (1, N) or all stereo (2, N)")
+    channels = next(iter(chans))
+    host, offsets, n_samples = pack_host(tracks, channels)
+    dev = torch.empty(host.numel(), dtype=torch.float32, device=f"cuda:{plan.device}")
+    dev.copy_(host, non_blocking=True)
+    return DeviceBatch(plan, dev, offsets, n_samples, channels)
+
+
+class FrontendBuffers:
+    """Device output buffers (torch-owned) for one DeviceBatch and the matching C struct."""
+
+    def __init__(self, batch: DeviceBatch, outputs: Iterable[str]):
+        plan = batch.plan
+        dev = batch.pcm.device
+        P, nt, B, M = batch.total_pitch, batch.n_tracks, plan.n_bins, plan.n_mels
+        outputs = set(outputs)
+        unknown = outputs - set(ALL_OUTPUTS)
+        if unknown:
+            raise ValueError(f"unknown outputs {sorted(unknown)}")
+        if outputs & {"onset_env", "autocorr", "flux_linear"}:
+            outputs.add("mel")
+        if "autocorr" in outputs:
+            outputs.add("onset_env")
+        max_ns = int(batch.n_samples.max()) if nt else 0
+        self.kw_pitch = max(1, plan.kw_block_count(max_ns))
+        self.rms_pitch = 1 + max_ns // plan.rms_frames(plan.meter_block)[1]
+        shapes = {
+            "magnitude": ((B * P,), torch.float32), "mel": ((M * P,), torch.float32),
+            "onset_env": ((P,), torch.float32), "autocorr": ((P,), torch.float64),
+            "flux_linear": ((P,), torch.float64), "ltas": ((nt, B), torch.float64),
+            "centroid": ((P,), torch.float64), "rolloff_bin": ((P,), torch.int32),
+            "band_energy": ((nt, 2, B), torch.float64), "moments": ((nt, 8), torch.float64),
+            "kw_blocks": ((nt, self.kw_pitch), torch.float64), "lufs": ((nt,), torch.float64),
+            "rms_momentary": ((nt, self.rms_pitch), torch.float64), "rms_short": ((nt, self.rms_pitch), torch.float64),
+        }
+        self.t = {k: torch.empty(shapes[k][0], dtype=shapes[k][1], device=dev) for k in ALL_OUTPUTS if k in outputs}
+        self.c_out = nat.FrontendOut()
+        for k in ALL_OUTPUTS:
+            setattr(self.c_out, k, self.t[k].data_ptr() if k in self.t else None)
+        self.c_out.kw_pitch = self.kw_pitch
+        self.c_out.rms_pitch = self.rms_pitch
+        self.outputs = outputs
+
+    def bytes_d2h(self) -> int:
+        return sum(t.numel() * t.element_size() for t in self.t.values())
+
+
+def workspace(plan: Plan, batch: DeviceBatch) -> torch.Tensor:
+    need = plan.lib.ta_workspace_bytes(plan._h, C.byref(batch.c_batch))
+    if need == 0:
+        nat.check(nat.TA_ERR_INVALID)
+    if plan._ws is None or plan._ws.numel() < need or plan._ws.device != batch.pcm.device:
+        plan._ws = torch.empty(need, dtype=torch.uint8, device=batch.pcm.device)
+    return plan._ws
+
+
+def run_device(plan: Plan, batch: DeviceBatch, bufs: FrontendBuffers, stage: str = "frontend") -> None:
+    """Enqueue the fused frontend (or one stage) on torch's current stream."""
+    ws = workspace(plan, batch)
+    stream = C.c_void_p(torch.cuda.current_stream(batch.pcm.device).cuda_stream)
+    fn = {"frontend": plan.lib.ta_frontend_run, "stft": plan.lib.ta_stft_features,
+          "time": plan.lib.ta_time_domain}[stage]
+    nat.check(fn(plan._h, C.byref(batch.c_batch), C.byref(bufs.c_out), C.c_void_p(ws.data_ptr()), ws.numel(), stream))
+
+
+def download(batch: DeviceBatch, bufs: FrontendBuffers) -> list[TrackResult]:
+    """Copy results to the host and cut them into per-track numpy arrays of reference shape."""
+    plan = batch.plan
+    host = {k: v.cpu().numpy() for k, v in bufs.t.items()}
+    B, M = plan.n_bins, plan.n_mels
+    out = []
+    for i in range(batch.n_tracks):
+        T, ld, po = int(batch.n_frames[i]), int(batch.pitch[i]), int(batch.pitch_off[i])
+        ns = int(batch.n_samples[i])
+        r = TrackResult(n_samples=ns, n_frames=T)
+        for k, h in host.items():
+            if k == "magnitude":
+                r.data[k] = h[B * po: B * (po + ld)].reshape(B, ld)[:, :T]
+            elif k == "mel":
+                r.data[k] = h[M * po: M * (po + ld)].reshape(M, ld)[:, :T]
+            elif k in ("onset_env", "autocorr", "flux_linear", "centroid", "rolloff_bin"):
+                r.data[k] = h[po: po + T]
+            elif k == "kw_blocks":
+                r.data[k] = h[i, : plan.kw_block_count(ns)]
+            elif k == "rms_momentary":
+                r.data[k] = h[i, : 1 + ns // plan.rms_frames(plan.meter_block)[1]]
+            elif k == "rms_short":
+                r.data[k] = h[i, : 1 + ns // plan.rms_frames(3.0)[1]]
+            elif k == "lufs":
+                r.data[k] = float(h[i])
+            else:
+                r.data[k] = h[i]
+        if "ltas" in r.data:
+            r.data["ltas"] = (r.data["ltas"] / T).astype(np.float32)
+        out.append(r)
+    return out
+
+
+def analyse_batch(plan: Plan, tracks: Sequence[np.ndarray], outputs: Iterable[str] = DEFAULT_OUTPUTS) -> list[TrackResult]:
+    """Host arrays in, host results out: H2D copy, fused frontend, D2H copy."""
+    batch = upload(plan, tracks)
+    bufs = FrontendBuffers(batch, outputs)
+    run_device(plan, batch, bufs)
+    return download(batch, bufs)
