@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the B200 spectral frontend (BASELINE.json metric: audio-seconds / second).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU oracle port on the host cores
+
+Workload (config.workload): BASELINE.json configs[2] sharded by track -- per GPU a
+batch of 3-minute 44.1 kHz stereo tracks, n_fft 2048, hop 512, 128 mels (the
+per-track shape of configs[1]); 128 tracks per GPU, i.e. 1024 tracks on 8 GPUs.
+One step = one pass of the whole frontend (ta_frontend_run: STFT magnitude, mel,
+LTAS/centroid/roll-off, stereo band energies, onset flux, autocorrelation,
+K-weighted gated loudness, RMS frames, moments) over that batch.
+
+  value   : tracks resident in HBM (8 GB per GPU >> 126 MB L2, so every step
+            streams from HBM), device time by CUDA events, max over ranks.
+  e2e     : the same work through engine.HostPipeline -- pinned host PCM copied
+            H2D every step and every output copied D2H inside the timed region.
+  roofline: the fused STFT kernel (dominant), algorithmic bytes / its event time.
+  cpu_baseline: the oracle port (oracle/, numpy+scipy) timed on the host cores.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SR, N_FFT, HOP, N_MELS = 44_100, 2048, 512, 128
+METRIC = "audio_seconds_per_second"
+UNIT = "audio-s/s (xRT)"
+
+
+# ----------------------------------------------------------------------------- CPU side
+def _gen_track(args):
+    seed, seconds = args
+    from track_analyser_b200 import synth
+
+    return synth.synth_track(seed, seconds, SR, 2)
+
+
+def _oracle_frontend(x):
+    """The reference's frontend arithmetic for one stereo track, every STFT computed once
+    (the reference itself recomputes the mono STFT >= 11 times)."""
+    from oracle import frontend as ofe
+    from oracle import librosa_np as olr
+    from oracle import pyloudnorm_np as opl
+
+    mono = np.mean(x, axis=0)
+    D = olr.stft(mono, n_fft=N_FFT, hop_length=HOP)
+    mag = np.abs(D)
+    mel = np.einsum("ft,mf->mt", mag**2, olr.filters_mel(SR, N_FFT, n_mels=N_MELS), optimize=True)
+    env = olr.onset_strength(S=olr.power_to_db(mel), sr=SR, hop_length=HOP)
+    out = [np.mean(mag, axis=1), olr.autocorrelate(env),
+           olr.onset_strength(S=np.asarray(mel, dtype=float), sr=SR, hop_length=HOP)]
+    freq = olr.fft_frequencies(SR, N_FFT)[:, None]
+    out.append(np.sum(freq * olr.normalize(mag, norm=1, axis=-2), axis=-2))
+    total = np.cumsum(mag, axis=-2)
+    out.append(np.nanmin(np.where(total < 0.85 * total[-1], np.nan, 1) * freq, axis=-2))
+    out.append(ofe.frequency_dependent_width(x, SR))
+    out.append(ofe.mid_side_rms(x))
+    out.append(ofe.mono_compatibility_correlation(x))
+    out.append(opl.integrated_loudness(mono, SR))
+    out.append(ofe.windowed_loudness(mono, SR, 0.4))
+    out.append(ofe.windowed_loudness(mono, SR, 3.0))
+    out.append(ofe.rms_dbfs(mono))
+    return len(out)
+
+
+def _oracle_timed(args):
+    seed, seconds = args
+    x = _gen_track((seed, seconds))
+    t0 = time.perf_counter()
+    _oracle_frontend(x)
+    return time.perf_counter() - t0
+
+
+def cpu_workers(world: int = 1) -> int:
+    return max(1, min(16, (os.cpu_count() or 1) // max(1, world)))
+
+
+def run_cpu_sample(workers: int, seconds: float, rounds: int = 1):
+    """`workers` processes, one `seconds`-long track each per round, all at once.
+
+    Each worker times only its oracle call (track synthesis excluded); a round's wall time
+    is the slowest worker's.  Returns (audio_seconds, wall_seconds)."""
+    ctx = mp.get_context("fork")
+    wall = 0.0
+    with ctx.Pool(workers) as pool:
+        for r in range(rounds):
+            dts = pool.map(_oracle_timed, [(13_370 + r * workers + i, seconds) for i in range(workers)], chunksize=1)
+            wall += max(dts)
+    return workers * rounds * seconds, max(wall, 1e-9)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self._stop = index, [], threading.Event()
+        self.th = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                    str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.samples.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples for i in range(4) if len(s) > 2 + i and s[2 + i] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    workers = cpu_workers(1)
+    seconds = args.ref_seconds
+    vals = []
+    for step in range(args.warmup + args.steps):
+        audio, wall = run_cpu_sample(workers, seconds)
+        if step >= args.warmup:
+            vals.append((audio, wall))
+    audio = sum(a for a, _ in vals)
+    wall = sum(w for _, w in vals)
+    v = audio / wall
+    sample = f"{workers} tracks x {seconds:.0f} s per step, one process per track (oracle port, STFTs shared)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {
+        "workload": ("BASELINE configs[2] sharded by track: %d tracks/GPU x %d GPU(s) of %.0f s 44.1 kHz stereo, "
+                     "n_fft 2048 hop 512 128 mels (per-track shape of configs[1]); full frontend, all outputs"
+                     % (args.tracks_per_gpu, world, args.seconds)),
+        "tracks_per_gpu": args.tracks_per_gpu, "seconds_per_track": args.seconds, "sample_rate": SR,
+        "n_fft": N_FFT, "hop": HOP, "n_mels": N_MELS,
+        "l2_policy": "inputs larger than L2 (%.1f GB PCM per GPU per step)" % (args.tracks_per_gpu * args.seconds * SR * 8 / 1e9),
+        "parallelism": f"tracks sharded over {world} GPU(s), no collective",
+    }
+
+
+# ----------------------------------------------------------------------------- our arm
+def ours(args, rank, world, local_rank):
+    workers = cpu_workers(world)
+    # 1. host pool of distinct synthetic tracks (and, on rank 0 at N=1, the CPU baseline) BEFORE CUDA init: fork-safe
+    pool_n = min(args.pool, args.tracks_per_gpu)
+    ctx = mp.get_context("fork")
+    with ctx.Pool(min(workers, pool_n)) as pool:
+        host_np = pool.map(_gen_track, [(13_370 + rank * args.tracks_per_gpu + i, args.seconds) for i in range(pool_n)])
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        audio, wall = run_cpu_sample(workers, args.ref_seconds)
+        cpu_baseline = {"value": audio / wall, "unit": UNIT, "cores": workers, "kind": "port",
+                        "sample": f"{workers} tracks x {args.ref_seconds:.0f} s, one process per track (oracle port, STFTs shared)"}
+
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+    from track_analyser_b200 import engine
+
+    dev = torch.device(f"cuda:{local_rank}")
+    plan = engine.Plan(SR, N_FFT, HOP, N_MELS, device=local_rank)
+    n = host_np[0].shape[1]
+    stride = (2 * n + 3) & ~3
+    host_pool = []
+    for x in host_np:
+        t = torch.empty(2 * n, dtype=torch.float32, pin_memory=True)
+        t.numpy()[:] = x.reshape(-1)
+        host_pool.append(t)
+    del host_np
+
+    # 2. resident batch: tracks_per_gpu tracks in HBM (pool repeated)
+    nt = args.tracks_per_gpu
+    pcm = torch.empty(nt * stride, dtype=torch.float32, device=dev)
+    for i in range(nt):
+        pcm[i * stride: i * stride + 2 * n].copy_(host_pool[i % pool_n], non_blocking=True)
+    batch = engine.DeviceBatch(plan, pcm, np.arange(nt, dtype=np.int64) * stride, np.full(nt, n, dtype=np.int64), 2)
+    bufs = engine.FrontendBuffers(batch, engine.ALL_OUTPUTS)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    audio_per_step = nt * args.seconds
+    # ---- kernel leg -------------------------------------------------------------------
+    for _ in range(args.warmup):
+        engine.run_device(plan, batch, bufs)
+    barrier()
+    launches0 = engine.launch_count()
+    stage = np.zeros(4)
+    with ClockSampler(local_rank) as clk:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            stage += np.asarray(engine.run_device_profiled(plan, batch, bufs))
+        e1.record()
+        barrier()
+        ms_kernel = e0.elapsed_time(e1) / args.steps
+    launches = engine.launch_count() - launches0
+    stage /= args.steps
+    t = torch.tensor([ms_kernel], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_kernel_max = float(t.item())
+    lufs = bufs.t["lufs"].cpu().numpy()
+    assert np.all(np.isfinite(lufs)), "frontend produced non-finite loudness"
+
+    # ---- end-to-end leg ------------------------------------------------------------------
+    chunk = min(args.chunk_tracks, nt)
+    del bufs, batch, pcm
+    torch.cuda.empty_cache()
+    pipe = engine.HostPipeline(plan, n, 2, chunk, engine.ALL_OUTPUTS)
+    tracks = [host_pool[i % pool_n] for i in range(nt)]
+    sink = []
+
+    def consume(ci, first, cnt, host_out):
+        sink.append(float(host_out["lufs"][:cnt].sum()))  # host reads the step's result
+
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    for _ in range(min(args.warmup, 1) or 1):
+        pipe.run(tracks, consume)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        pipe.run(tracks, consume)
+    barrier()
+    s_e2e = (time.perf_counter() - t0) / e2e_steps
+    t = torch.tensor([s_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    s_e2e_max = float(t.item())
+    n_chunks = (nt + chunk - 1) // chunk
+
+    if rank == 0:
+        B = N_FFT // 2 + 1
+        T = 1 + n // HOP
+        k1_bytes = nt * (4 * 2 * n + 4 * B * T + 4 * N_MELS * T + 12 * T)  # PCM read + magnitude + mel + centroid/roll-off
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = k1_bytes / (stage[0] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": world * audio_per_step / (ms_kernel_max * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_kernel_max, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "stage_ms": {"stft_mel_features": stage[0], "onset_flux": stage[1], "autocorrelation": stage[2],
+                         "time_domain_loudness": stage[3]},
+            "roofline": {"bound": "hbm", "kernel": "stft_fused_kernel<2048,32,stereo>", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                         "algorithmic_bytes_per_launch": k1_bytes},
+            "e2e": {"value": world * audio_per_step / s_e2e_max, "unit": UNIT,
+                    "h2d_bytes_per_step": nt * 2 * n * 4, "d2h_bytes_per_step": n_chunks * pipe.d2h_bytes_per_chunk,
+                    "steps": e2e_steps, "s_per_step": s_e2e_max, "chunk_tracks": chunk},
+            "gpu_launches": int(launches),
+            "clocks": clk.summary(),
+        }
+        if cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tracks-per-gpu", type=int, default=128)
+    ap.add_argument("--pool", type=int, default=16, help="distinct synthetic tracks per GPU (cycled to fill the batch)")
+    ap.add_argument("--seconds", type=float, default=180.0)
+    ap.add_argument("--chunk-tracks", type=int, default=8)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-seconds", type=float, default=60.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+    else:
+        ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

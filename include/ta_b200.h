@@ -126,6 +126,17 @@ TA_API size_t ta_workspace_bytes(const ta_plan* plan, const ta_batch* batch);
 TA_API int ta_frontend_run(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* Same schedule as ta_frontend_run, but brackets each stage with CUDA events on
+ * `stream`, synchronises, and returns the device time of each stage in
+ * milliseconds: stage_ms[0] STFT+mel+features (K1/K2/K7), [1] onset flux (K3),
+ * [2] autocorrelation (K4), [3] time-domain pass + gating (K5/K6).  For bench.py's
+ * roofline figure; not for production use (it blocks the host). */
+TA_API int ta_frontend_run_profiled(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out,
+                                    void* workspace, size_t workspace_bytes, void* stream, float stage_ms[4]);
+
+/* Number of kernels this library has launched in the calling process so far. */
+TA_API uint64_t ta_launch_count(void);
+
 /* --- single-stage entry points (each is also a step of ta_frontend_run) ------ */
 
 /* K1+K2+K7: fused frame + Hann + FFT + |X| (+ mel, LTAS, centroid, roll-off, band sums).

@@ -1,0 +1,300 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Run with -m gpu.
+
+Tolerances (north star): spectra and features rtol 1e-4 / atol 1e-6 in fp32,
+integrated loudness within 0.01 LU, integer outputs bit-exact.  Two documented
+deviations, both measured in profiles/ and DESIGN.md:
+  * the fp32 FFT's absolute error scales with the *frame's* energy (about
+    1.2e-7 * ||w*x||_2), so bins more than ~100 dB below the frame peak can miss
+    atol 1e-6; magnitude is therefore checked as pass-rate >= 99.999 % at the
+    north-star tolerance plus a strict bound relative to the frame energy;
+  * roll-off is `first bin where cumsum >= 0.85 * total`, an integer decision
+    on float32 sums: a near-tie may move it by one bin (>= 99.5 % equal required).
+"""
+
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(), reason="needs a CUDA device")]
+
+from oracle import frontend as ofe  # noqa: E402
+from oracle import librosa_np as olr  # noqa: E402
+from oracle import pyloudnorm_np as opl  # noqa: E402
+from track_analyser_b200 import _native as nat  # noqa: E402
+from track_analyser_b200 import engine, hostlogic, loudness_host, stereo as pstereo, synth  # noqa: E402
+from track_analyser_b200 import tempo as ptempo  # noqa: E402
+
+from . import signals  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+RTOL, ATOL = 1e-4, 1e-6
+
+_plans = {}
+
+
+def plan_for(sr, n_fft=2048, hop=512, n_mels=128):
+    key = (sr, n_fft, hop, n_mels)
+    if key not in _plans:
+        _plans[key] = engine.Plan(sr, n_fft, hop, n_mels, device=0)
+    return _plans[key]
+
+
+def pass_rate(got, ref, rtol=RTOL, atol=ATOL):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape
+    return float(np.mean(np.abs(got - ref) <= atol + rtol * np.abs(ref))) if ref.size else 1.0
+
+
+def oracle_outputs(x, sr, n_fft=2048, hop=512, n_mels=128):
+    st = np.asarray(x, dtype=np.float32)
+    mono = np.mean(st, axis=0) if st.ndim == 2 else st
+    mag = np.abs(olr.stft(mono, n_fft=n_fft, hop_length=hop))
+    mel = np.einsum("ft,mf->mt", mag**2, olr.filters_mel(sr, n_fft, n_mels=n_mels), optimize=True)
+    env = olr.onset_strength(S=olr.power_to_db(mel), sr=sr, hop_length=hop)
+    return dict(mono=mono, magnitude=mag, mel=mel, onset_env=env, autocorr=olr.autocorrelate(env),
+                flux_linear=olr.onset_strength(S=np.asarray(mel, dtype=float), sr=sr, hop_length=hop),
+                ltas=np.mean(mag, axis=1), centroid=olr.spectral_centroid(mono, sr, n_fft, hop)[0],
+                rolloff=olr.spectral_rolloff(mono, sr, n_fft, hop)[0])
+
+
+def check_track(res, x, sr, n_fft=2048, hop=512, n_mels=128, loud=True):
+    o = oracle_outputs(x, sr, n_fft, hop, n_mels)
+    mono = o["mono"]
+    # magnitude: north-star tolerance on >= 99.999 % of the bins, strict bound relative to the frame energy
+    assert pass_rate(res["magnitude"], o["magnitude"]) >= 0.99999
+    frame_norm = np.sqrt(np.sum(o["magnitude"].astype(np.float64) ** 2, axis=0, keepdims=True) * 2 / n_fft)
+    err = np.abs(res["magnitude"].astype(np.float64) - o["magnitude"])
+    assert np.all(err <= 1e-6 + 1e-4 * o["magnitude"] + 1.5e-6 * frame_norm)
+    np.testing.assert_allclose(res["mel"], o["mel"], rtol=RTOL, atol=ATOL * max(1.0, float(o["mel"].max())))
+    np.testing.assert_allclose(res["onset_env"], o["onset_env"], rtol=RTOL, atol=5e-6)
+    np.testing.assert_allclose(res["autocorr"], o["autocorr"], rtol=RTOL, atol=1e-6 * max(1.0, float(o["autocorr"][0])))
+    np.testing.assert_allclose(res["flux_linear"], o["flux_linear"], rtol=RTOL, atol=ATOL * max(1.0, float(o["mel"].max())))
+    np.testing.assert_allclose(res["ltas"], o["ltas"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(res["centroid"], o["centroid"], rtol=RTOL, atol=1e-3)
+    freqs = np.fft.rfftfreq(n_fft, 1.0 / sr)
+    assert np.mean(freqs[res["rolloff_bin"]] == o["rolloff"]) >= 0.995
+    assert np.max(np.abs(freqs[res["rolloff_bin"]] - o["rolloff"])) <= sr / n_fft + 1e-9
+    # integer outputs derived from the envelope: bit-exact
+    np.testing.assert_array_equal(hostlogic.onset_detect(res["onset_env"], sr, hop, backtrack=True),
+                                  hostlogic.onset_detect(o["onset_env"], sr, hop, backtrack=True))
+    if loud and mono.size >= 0.4 * sr:
+        assert abs(res["lufs"] - opl.integrated_loudness(mono, sr)) < 0.01
+        np.testing.assert_allclose(res["kw_blocks"], opl.block_energies(mono, sr), rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(loudness_host.frames_to_db(res["rms_momentary"]), ofe.windowed_loudness(mono, sr, 0.4),
+                               rtol=RTOL, atol=1e-4)
+    np.testing.assert_allclose(loudness_host.frames_to_db(res["rms_short"]), ofe.windowed_loudness(mono, sr, 3.0),
+                               rtol=RTOL, atol=1e-4)
+    st = np.asarray(x, dtype=np.float32)
+    if st.ndim == 2:
+        np.testing.assert_allclose(pstereo.mid_side_from_moments(res["moments"]), ofe.mid_side_rms(st), rtol=RTOL, atol=ATOL)
+        assert pstereo.correlation_from_moments(res["moments"]) == pytest.approx(ofe.mono_compatibility_correlation(st), abs=1e-5)
+        w = pstereo.width_from_band_energy(res["band_energy"], freqs, res.n_frames, None, sr)
+        ref = ofe.frequency_dependent_width(st, sr, n_fft=n_fft, hop_length=hop)
+        for k in ("low", "mid", "high"):
+            assert w[k] == pytest.approx(ref[k], rel=RTOL, abs=ATOL)
+
+
+# ------------------------------------------------------------------------------ batches
+def test_stereo_ragged_batch_matches_oracle():
+    sr = 44_100
+    tracks = [synth.synth_track(synth.DEFAULT_SEED + i, 6.0 + 2.3 * i, sr, 2) for i in range(3)]
+    before = engine.launch_count()
+    res = engine.analyse_batch(plan_for(sr), tracks, engine.ALL_OUTPUTS)
+    assert engine.launch_count() - before >= 5  # our kernels ran
+    for r, x in zip(res, tracks):
+        check_track(r, x, sr)
+
+
+def test_mono_batch_matches_oracle_48k():
+    sr = 48_000
+    tracks = [synth.synth_track(100 + i, 5.0 + i, sr, 1) for i in range(2)]
+    for r, x in zip(engine.analyse_batch(plan_for(sr), tracks, engine.ALL_OUTPUTS), tracks):
+        check_track(r, x, sr)
+
+
+def test_config5_shape_4096_256_mels():
+    sr = 44_100
+    x = synth.synth_track(5, 4.0, sr, 2)
+    res = engine.analyse_batch(plan_for(sr, 4096, 256, 256), [x], ("magnitude", "mel", "ltas", "centroid", "rolloff_bin"))[0]
+    o = oracle_outputs(x, sr, 4096, 256, 256)
+    assert pass_rate(res["magnitude"], o["magnitude"]) >= 0.99999
+    np.testing.assert_allclose(res["mel"], o["mel"], rtol=RTOL, atol=ATOL * float(o["mel"].max()))
+    np.testing.assert_allclose(res["ltas"], o["ltas"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(res["centroid"], o["centroid"], rtol=RTOL, atol=1e-3)
+
+
+def test_n_fft_1024():
+    sr = 22_050
+    x = synth.synth_track(9, 3.0, sr, 1)
+    res = engine.analyse_batch(plan_for(sr, 1024, 256, 64), [x], ("magnitude", "mel"))[0]
+    o = oracle_outputs(x, sr, 1024, 256, 64)
+    assert pass_rate(res["magnitude"], o["magnitude"]) >= 0.99999
+    np.testing.assert_allclose(res["mel"], o["mel"], rtol=RTOL, atol=ATOL * float(o["mel"].max()))
+
+
+def test_golden_fixtures():
+    sr = 44_100
+    g = np.load(os.path.join(GOLDEN, "tiny_click.npz"))
+    r = engine.analyse_batch(plan_for(sr), [g["samples"]], engine.ALL_OUTPUTS)[0]
+    assert r.n_frames == 175  # BASELINE configs[0]: N = 89 523
+    np.testing.assert_allclose(r["onset_env"], g["onset_env"], rtol=RTOL, atol=5e-6)
+    np.testing.assert_allclose(r["autocorr"], g["autocorr"], rtol=RTOL, atol=1e-6 * float(g["autocorr"][0]))
+    np.testing.assert_allclose(r["ltas"], g["ltas"], rtol=RTOL, atol=ATOL)
+    np.testing.assert_allclose(r["mel"], g["mel"], rtol=RTOL, atol=ATOL * float(g["mel"].max()))
+    np.testing.assert_allclose(r["magnitude"][::64], g["magnitude_rows"], rtol=RTOL, atol=2e-6)
+    assert abs(r["lufs"] - float(g["lufs"])) < 0.01
+    np.testing.assert_allclose(r["kw_blocks"], g["kw_blocks"], rtol=RTOL, atol=1e-12)
+    g2 = np.load(os.path.join(GOLDEN, "synth_stereo_4s.npz"))
+    r2 = engine.analyse_batch(plan_for(sr), [g2["stereo"]], engine.ALL_OUTPUTS)[0]
+    np.testing.assert_allclose(r2["onset_env"], g2["onset_env"], rtol=RTOL, atol=5e-6)
+    np.testing.assert_allclose(pstereo.mid_side_from_moments(r2["moments"]), g2["mid_side_rms"], rtol=RTOL)
+    freqs = np.fft.rfftfreq(2048, 1.0 / sr)
+    w = pstereo.width_from_band_energy(r2["band_energy"], freqs, r2.n_frames, None, sr)
+    np.testing.assert_allclose([w["low"], w["mid"], w["high"]], g2["width"], rtol=RTOL)
+    assert abs(r2["lufs"] - float(g2["lufs"])) < 0.01
+
+
+# ------------------------------------------------------------------------------ edge cases
+@pytest.mark.parametrize("name", ["silence", "dc", "square", "short", "impulse"])
+def test_edge_inputs(name):
+    sr = 44_100
+    n = sr
+    x = {"silence": np.zeros(n, np.float32), "dc": np.full(n, 0.25, np.float32),
+         "square": np.where(np.arange(n) % 100 < 50, 1.0, -1.0).astype(np.float32),
+         "short": signals.sine(440.0, sr, 0.01), "impulse": np.eye(1, n, n // 2, dtype=np.float32)[0]}[name]
+    outs = engine.ALL_OUTPUTS if x.size >= 0.4 * sr else tuple(o for o in engine.ALL_OUTPUTS if o not in ("lufs", "kw_blocks"))
+    r = engine.analyse_batch(plan_for(sr), [x], outs)[0]
+    o = oracle_outputs(x, sr)
+    assert r["magnitude"].shape == o["magnitude"].shape
+    frame_norm = np.sqrt(np.sum(o["magnitude"].astype(np.float64) ** 2, axis=0, keepdims=True) * 2 / 2048)
+    err = np.abs(r["magnitude"].astype(np.float64) - o["magnitude"])
+    assert np.all(err <= 1e-6 + 1e-4 * o["magnitude"] + 1.5e-6 * frame_norm)
+    # |X| of fp32 rounding noise is positive, so near-empty bins of loud frames bias the time mean upwards
+    np.testing.assert_allclose(r["ltas"], o["ltas"], rtol=RTOL, atol=1e-6 + 1.5e-6 * float(frame_norm.mean()))
+    if name == "silence":
+        assert np.all(r["magnitude"] == 0) and np.all(r["onset_env"] == 0) and np.all(r["rolloff_bin"] == 0)
+        assert r["lufs"] == -np.inf and opl.integrated_loudness(x, sr) == -np.inf
+    elif "lufs" in r:
+        assert abs(r["lufs"] - opl.integrated_loudness(x, sr)) < 0.01
+
+
+def test_channel_layouts_agree():
+    sr = 44_100
+    mono = synth.synth_track(3, 2.0, sr, 1)
+    a = engine.analyse_batch(plan_for(sr), [mono], ("magnitude", "mel"))[0]
+    b = engine.analyse_batch(plan_for(sr), [mono[None, :]], ("magnitude", "mel"))[0]
+    np.testing.assert_array_equal(a["magnitude"], b["magnitude"])
+    # duplicated channels: mid == mono exactly, side == 0
+    c = engine.analyse_batch(plan_for(sr), [np.vstack([mono, mono])], ("magnitude", "band_energy", "moments"))[0]
+    np.testing.assert_allclose(c["magnitude"], a["magnitude"], rtol=1e-4, atol=1e-5)
+    # side spectrum: zero up to the (non-Hermitian) rounding of the packed complex FFT; side in time: exactly 0
+    assert c["band_energy"][1].max() <= 1e-10 * c["band_energy"][0].max() and c["moments"][6] == 0
+
+
+# ------------------------------------------------------------------------------ size-independent properties
+def test_full_size_properties_config2():
+    """3-minute 44.1 kHz stereo track (BASELINE configs[1]): exact scaling, Parseval, batch independence."""
+    sr = 44_100
+    x = synth.synth_track(synth.DEFAULT_SEED, 180.0, sr, 2)
+    plan = plan_for(sr)
+    r1 = engine.analyse_batch(plan, [x], engine.ALL_OUTPUTS)[0]
+    assert r1.n_frames == 15_504 and r1["magnitude"].shape == (1025, 15_504)
+    # linearity with a power-of-two gain is exact in binary floating point
+    r2 = engine.analyse_batch(plan, [0.5 * x], ("magnitude", "mel", "lufs", "ltas"))[0]
+    np.testing.assert_array_equal(r2["magnitude"], 0.5 * r1["magnitude"])
+    np.testing.assert_array_equal(r2["mel"], 0.25 * r1["mel"])
+    assert r2["lufs"] == pytest.approx(r1["lufs"] + 20 * np.log10(0.5), abs=1e-6)
+    # Parseval: sum over frames/bins of the one-sided power equals the windowed signal energy
+    mono = np.mean(x, axis=0).astype(np.float64)
+    w2 = olr.get_window("hann", 2048) ** 2
+    cover = np.zeros(mono.size + 2048)
+    for t in range(r1.n_frames):
+        cover[t * 512: t * 512 + 2048] += w2
+    time_energy = float(np.sum(cover[1024: 1024 + mono.size] * mono**2))
+    be = r1["band_energy"][0]
+    freq_energy = float((be[0] + be[-1] + 2.0 * be[1:-1].sum()) / 2048)
+    assert freq_energy == pytest.approx(time_energy, rel=2e-6)
+    # tracks in a batch do not influence each other
+    other = synth.synth_track(77, 31.0, sr, 2)
+    rb = engine.analyse_batch(plan, [other, x], ("magnitude", "mel", "onset_env", "autocorr", "rolloff_bin"))[1]
+    for k in ("magnitude", "mel", "onset_env", "autocorr", "rolloff_bin"):
+        np.testing.assert_array_equal(rb[k], r1[k])
+    # oracle at full size for the headline tensors
+    o = oracle_outputs(x, sr)
+    assert pass_rate(r1["magnitude"], o["magnitude"]) >= 0.99999
+    np.testing.assert_allclose(r1["onset_env"], o["onset_env"], rtol=RTOL, atol=5e-6)
+    np.testing.assert_allclose(r1["autocorr"], o["autocorr"], rtol=RTOL, atol=1e-6 * float(o["autocorr"][0]))
+    assert abs(r1["lufs"] - opl.integrated_loudness(np.mean(x, axis=0), sr)) < 0.01
+    env_o, ac_o = o["onset_env"], o["autocorr"]
+    assert ptempo._bpm_from_autocorr(r1["onset_env"], r1["autocorr"], sr, 90.0, 135.0, 512) == pytest.approx(
+        ptempo._bpm_from_autocorr(env_o, ac_o, sr, 90.0, 135.0, 512), rel=1e-9)
+
+
+# ------------------------------------------------------------------------------ reference-shaped API
+def test_module_api_like_reference_tests():
+    from track_analyser_b200 import features, stereo
+    from track_analyser_b200.analysis import loudness
+    from track_analyser_b200.utils import AudioInput
+
+    tone = signals.sine(440.0)
+    ltas = features.compute_ltas(tone, 22_050)  # reference test_features.py:15-24
+    assert float(ltas.frequencies[np.argmax(ltas.magnitude)]) == pytest.approx(440.0, abs=5.0)
+    assert features.spectral_centroid_series(signals.sine(1000.0), 22_050).mean == pytest.approx(1000.0, abs=20.0)
+    noise = np.random.default_rng(1337).normal(size=22_050).astype(np.float32)
+    assert np.all(features.spectral_rolloff_series(noise, 22_050).values > 5_000.0)
+    fa = features.analyse_features(AudioInput(samples=tone, sample_rate=22_050))
+    assert fa.ltas.frequencies.shape == fa.ltas.magnitude.shape and fa.spectral_rolloff.values.ndim == 1
+    sa = stereo.analyse_stereo(AudioInput(samples=tone, sample_rate=22_050))  # test_stereo.py:15-27
+    assert sa.side_rms == pytest.approx(0.0, abs=1e-6) and sa.correlation == pytest.approx(1.0, abs=1e-6)
+    assert max(sa.width.low, sa.width.mid, sa.width.high) == pytest.approx(0.0, abs=1e-6)
+    m, s = stereo.mid_side_rms(np.vstack([tone, 0.5 * tone]))
+    assert m > s > 0.0
+    assert stereo.mono_compatibility_correlation(np.ones((2, 10), np.float32)) == pytest.approx(1.0)
+    x = signals.minus18_sine(48_000)  # test_loudness.py:33-43
+    integrated, short_term, momentary, lra = loudness.measure_loudness(x, 48_000)
+    assert integrated == pytest.approx(-18.0, abs=0.3) and short_term and momentary
+    res = loudness.analyse_loudness(AudioInput(samples=x, sample_rate=48_000), seed=0)
+    assert res.integrated_lufs == pytest.approx(integrated, abs=1e-6) and res.momentary_lufs == momentary
+    with pytest.raises(ValueError):
+        loudness.measure_loudness(np.zeros((2, 100), np.float32), 48_000)
+    with pytest.raises(TypeError):
+        loudness.analyse_loudness("file.wav", seed=0)
+
+
+def test_tempo_api_like_reference_test():
+    y, sr, expected = signals.noisy_click_track()  # test_tempo.py:39-53
+    assert abs(ptempo.estimate_bpm(y, sr) - 120.0) <= 0.1
+    grid = ptempo.beat_grid(y, sr)
+    assert grid.shape[0] >= expected.size
+    actual = grid["time"].to_numpy()[: expected.size]
+    assert float(np.max(np.abs(actual - expected[: actual.size]))) <= 0.005
+    # integer outputs identical to the oracle-driven host logic
+    env = ofe.onset_envelope(y, sr)
+    bpm = ptempo._bpm_from_autocorr(env, ofe.onset_autocorrelation(env), sr, 90.0, 135.0, 512)
+    fit = ptempo._fit_onset_regression(env, sr, 512, 60.0 / bpm)
+    start = max(fit[0], 0.0)
+    n = grid.shape[0]
+    ref_frames = hostlogic.time_to_frames(start + np.arange(n) * (60.0 / bpm), sr, 512)
+    np.testing.assert_array_equal(grid["frame"].to_numpy(), ref_frames)
+
+
+# ------------------------------------------------------------------------------ C-ABI error behaviour
+def test_abi_errors():
+    plan = plan_for(44_100)
+    lib = plan.lib
+    x = synth.synth_track(1, 1.0, 44_100, 2)
+    batch = engine.upload(plan, [x])
+    bufs = engine.FrontendBuffers(batch, ("magnitude",))
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.ta_frontend_run(plan._h, C.byref(batch.c_batch), C.byref(bufs.c_out), None, 0, stream)
+    assert rc == nat.TA_ERR_WORKSPACE and b"workspace" in lib.ta_last_error()
+    bad = nat.Batch(0, 2, batch.pcm.data_ptr(), batch.c_batch.pcm_offset, batch.c_batch.n_samples)
+    assert lib.ta_workspace_bytes(plan._h, C.byref(bad)) == 0
+    ws = engine.workspace(plan, batch)
+    rc = lib.ta_frontend_run(plan._h, C.byref(bad), C.byref(bufs.c_out), C.c_void_p(ws.data_ptr()), ws.numel(), stream)
+    assert rc == nat.TA_ERR_INVALID
+    with pytest.raises(ValueError):
+        engine.upload(plan, [x, x[0]])

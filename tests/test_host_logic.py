@@ -1,0 +1,109 @@
+"""Host-side glue of the product: peak picking, stereo sums, dB conversion, sharding, coercion."""
+
+import numpy as np
+import pytest
+
+from oracle import frontend as fe
+from oracle import librosa_np as lr
+from track_analyser_b200 import hostlogic, loudness_host, sharding, stereo, utils
+
+from . import signals
+
+
+def brute_peak_pick(x, pre_max, post_max, pre_avg, post_avg, delta, wait):
+    peaks, last = [], -10**9
+    for n in range(len(x)):
+        w = x[max(0, n - pre_max): n + post_max]
+        a = x[max(0, n - pre_avg): n + post_avg]
+        if x[n] == w.max() and x[n] >= a.astype(np.float64).mean() + delta and n > last + wait:
+            peaks.append(n)
+            last = n
+    return np.array(peaks, dtype=int)
+
+
+def test_peak_pick_matches_definition():
+    rng = np.random.default_rng(11)
+    for _ in range(5):
+        x = rng.random(400).astype(np.float32)
+        got = hostlogic.peak_pick(x, 2, 1, 8, 9, 0.07, 2)
+        np.testing.assert_array_equal(got, brute_peak_pick(x, 2, 1, 8, 9, 0.07, 2))
+
+
+def test_onset_backtrack_moves_to_previous_minimum():
+    e = np.array([3, 1, 2, 5, 4, 0.5, 0.7, 9], dtype=np.float32)
+    np.testing.assert_array_equal(hostlogic.onset_backtrack(np.array([3, 7]), e), [1, 5])
+    np.testing.assert_array_equal(hostlogic.onset_backtrack(np.array([0]), e), [0])
+
+
+def test_time_frame_round_trip():
+    t = np.array([0.0, 0.5, 1.2345])
+    np.testing.assert_array_equal(hostlogic.time_to_frames(t, 44_100, 512), (t * 44_100).astype(int) // 512)
+    assert hostlogic.frames_to_time(10, 44_100, 512) == 10 * 512 / 44_100
+
+
+def test_stereo_sums_reproduce_oracle():
+    st = np.vstack([signals.sine(440.0), 0.5 * signals.sine(523.0, phase=0.3)]).astype(np.float32)
+    L, R = st.astype(np.float64)
+    mid, side = 0.5 * (st[0] + st[1]), 0.5 * (st[0] - st[1])
+    m = [L.sum(), R.sum(), (L * L).sum(), (R * R).sum(), (L * R).sum(), (mid.astype(float) ** 2).sum(),
+         (side.astype(float) ** 2).sum(), float(L.size)]
+    np.testing.assert_allclose(stereo.mid_side_from_moments(m), fe.mid_side_rms(st), rtol=1e-6)
+    assert stereo.correlation_from_moments(m) == pytest.approx(fe.mono_compatibility_correlation(st), abs=1e-6)
+    ones = [10.0, 10.0, 10.0, 10.0, 10.0, 10.0, 0.0, 10.0]
+    assert stereo.correlation_from_moments(ones) == 1.0  # reference: test_stereo.py:57-64
+    # width from per-bin energy sums
+    DL, DR = lr.stft(st[0]), lr.stft(st[1])
+    be = np.stack([(np.abs(0.5 * (DL + DR)) ** 2).sum(axis=1), (np.abs(0.5 * (DL - DR)) ** 2).sum(axis=1)]).astype(float)
+    w = stereo.width_from_band_energy(be, lr.fft_frequencies(22_050, 2048), DL.shape[1], None, 22_050)
+    ref = fe.frequency_dependent_width(st, 22_050)
+    for k in ("low", "mid", "high"):
+        assert w[k] == pytest.approx(ref[k], rel=1e-5, abs=1e-9)
+
+
+def test_frames_to_db_matches_oracle():
+    x = signals.minus18_sine(44_100, seconds=3.0)
+    for seconds in (0.4, 3.0):
+        frame = max(1024, int(round(44_100 * seconds)))
+        frame += frame % 2
+        ms = lr.rms(x, frame_length=frame, hop_length=frame // 2)[0].astype(np.float64) ** 2
+        np.testing.assert_allclose(loudness_host.frames_to_db(ms), fe.windowed_loudness(x, 44_100, seconds),
+                                   rtol=1e-6, atol=1e-5)
+
+
+def test_partition_covers_every_track_once():
+    for lengths, world in (([100] * 10, 4), ([5, 9, 1, 7, 7, 3, 2], 3), ([4], 8), ([], 2)):
+        shards = sharding.partition(lengths, world)
+        assert len(shards) == world
+        assert sorted(i for s in shards for i in s) == list(range(len(lengths)))
+    eq = sharding.partition([7] * 1024, 8)
+    assert all(len(s) == 128 for s in eq) and eq[1][0] == 128
+    ragged = sharding.partition([10, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1], 2)
+    assert sum(l for i, l in enumerate([10] + [1] * 10) if i in ragged[0]) == 10
+
+
+def test_coerce_audio_shapes():
+    st = np.vstack([signals.sine(440.0), signals.sine(220.0)])
+    a = utils.coerce_audio(st)
+    assert a.sample_rate == utils.DEFAULT_SR and a.stereo_samples.shape == st.shape
+    np.testing.assert_array_equal(a.samples, np.mean(st, axis=0))
+    assert utils.coerce_audio(a).samples is not None and a.duration == st.shape[1] / 44_100
+    with pytest.raises(TypeError):
+        utils.coerce_audio(123)
+    with pytest.raises(NotImplementedError):
+        utils.coerce_audio(utils.AudioInput(st[0], 48_000))
+
+
+def test_wav_reader_round_trip(tmp_path):
+    import struct
+
+    from track_analyser_b200 import io as tio
+
+    x = (np.random.default_rng(0).uniform(-0.5, 0.5, size=(1000, 2)) * 32767).astype("<i2")
+    p = tmp_path / "t.wav"
+    with open(p, "wb") as fh:
+        data = x.tobytes()
+        fh.write(b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVEfmt " +
+                 struct.pack("<IHHIIHH", 16, 1, 2, 44_100, 44_100 * 4, 4, 16) + b"data" + struct.pack("<I", len(data)) + data)
+    s, sr, meta = tio.load_audio(str(p))
+    assert sr == 44_100 and s.shape == (2, 1000) and meta["channels"] == 2
+    np.testing.assert_array_equal(s, (x.astype(np.float32) / 32768.0).T)

@@ -88,6 +88,8 @@ SYMBOLS = {
     "ta_plan_table": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "ta_workspace_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(Batch)]),
     "ta_frontend_run": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(FrontendOut), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ta_frontend_run_profiled": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(FrontendOut), C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_float)]),
+    "ta_launch_count": (C.c_uint64, []),
     "ta_stft_features": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(FrontendOut), C.c_void_p, C.c_size_t, C.c_void_p]),
     "ta_onset_flux": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ta_autocorrelate": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -215,12 +215,15 @@ int run_autocorrelate(const ta_plan* plan, const HostBatch& hb, const TrackDesc*
     }
     if (max_n1 > 1) {
         ac_columns_kernel<false><<<dim3(max_cols_grid, hb.n_tracks), AC_THREADS, smem, stream>>>(d_tracks, env, d_work, d_off, out);
+        count_launch();
         TA_CUDA(cudaGetLastError());
     }
     ac_rows_kernel<<<dim3(max_n1, hb.n_tracks), AC_THREADS, smem, stream>>>(d_tracks, env, d_work, d_off, out);
+        count_launch();
     TA_CUDA(cudaGetLastError());
     if (max_n1 > 1) {
         ac_columns_kernel<true><<<dim3(max_cols_grid, hb.n_tracks), AC_THREADS, smem, stream>>>(d_tracks, env, d_work, d_off, out);
+        count_launch();
         TA_CUDA(cudaGetLastError());
     }
     return TA_OK;

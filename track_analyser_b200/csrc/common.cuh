@@ -11,6 +11,7 @@
 namespace ta {
 
 void set_error(const std::string& msg);
+void count_launch(int n = 1);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define TA_CUDA(expr)                                                         \

@@ -58,6 +58,7 @@ int run_onset_flux(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_
     const int pad = 1 + 2048 / (2 * plan->desc.hop);  // onset_strength's own n_fft default (tempo.py:19, structure.py:195)
     dim3 grid((hb.max_frames + 255) / 256, hb.n_tracks);
     onset_flux_kernel<<<grid, 256, 0, stream>>>(d_tracks, mel, mel_max, onset_env, flux_linear, plan->desc.n_mels, pad);
+    count_launch();
     TA_CUDA(cudaGetLastError());
     return TA_OK;
 }

@@ -1,5 +1,6 @@
 // Plan construction (host-side tables computed in double), error plumbing, batch
 // descriptors, workspace carve-up and the fused schedule of the C ABI.
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -9,6 +10,8 @@
 namespace ta {
 
 static thread_local std::string g_last_error;
+static std::atomic<uint64_t> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(uint64_t(n), std::memory_order_relaxed); }
 
 void set_error(const std::string& msg) { g_last_error = msg; }
 
@@ -416,28 +419,56 @@ int ta_time_domain(const ta_plan* plan, const ta_batch* batch, const ta_frontend
     return run_time_domain(plan, hb, ws, out, st);
 }
 
-int ta_frontend_run(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out, void* workspace,
-                    size_t workspace_bytes, void* stream) {
+uint64_t ta_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out, void* workspace,
+                         size_t workspace_bytes, void* stream, cudaEvent_t* ev) {
     TA_REQUIRE(out, "out must not be NULL");
     HostBatch hb;
     Workspace ws;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int rc = prepare(plan, batch, workspace, workspace_bytes, st, hb, ws);
     if (rc != TA_OK) return rc;
+    auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], st); };
+    mark(0);
     const bool need_flux = out->onset_env || out->flux_linear || out->autocorr;
     TA_REQUIRE(!need_flux || out->mel, "onset/autocorr outputs need the mel output buffer");
     TA_REQUIRE(!out->autocorr || out->onset_env, "autocorr output needs the onset_env output buffer");
     const bool need_stft = out->magnitude || out->mel || out->ltas || out->centroid || out->rolloff_bin || out->band_energy;
     if (need_stft && (rc = run_stft_features(plan, hb, ws, out, st)) != TA_OK) return rc;
+    mark(1);
     if (need_flux && (rc = run_onset_flux(plan, hb, ws.d_tracks, out->mel, ws.d_mel_max, out->onset_env,
                                           out->flux_linear, st)) != TA_OK)
         return rc;
+    mark(2);
     if (out->autocorr &&
         (rc = run_autocorrelate(plan, hb, ws.d_tracks, out->onset_env, out->autocorr, ws.d_fft, ws.fft_elems, st)) != TA_OK)
         return rc;
+    mark(3);
     const bool need_td = out->moments || out->kw_blocks || out->lufs || out->rms_momentary || out->rms_short;
     if (need_td && (rc = run_time_domain(plan, hb, ws, out, st)) != TA_OK) return rc;
+    mark(4);
     return TA_OK;
+}
+
+int ta_frontend_run(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+    return frontend_impl(plan, batch, out, workspace, workspace_bytes, stream, nullptr);
+}
+
+int ta_frontend_run_profiled(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out, void* workspace,
+                             size_t workspace_bytes, void* stream, float stage_ms[4]) {
+    TA_REQUIRE(stage_ms, "stage_ms must not be NULL");
+    cudaEvent_t ev[5];
+    for (auto& e : ev) TA_CUDA(cudaEventCreate(&e));
+    int rc = frontend_impl(plan, batch, out, workspace, workspace_bytes, stream, ev);
+    if (rc == TA_OK) {
+        cudaError_t e = cudaEventSynchronize(ev[4]);
+        if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventSynchronize", __FILE__, __LINE__);
+        for (int i = 0; i < 4 && rc == TA_OK; ++i) cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]);
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
 }
 
 }  // extern "C"

@@ -323,6 +323,7 @@ static int launch_stft(const ta_plan* plan, const StftParams& p, cudaStream_t st
     }
     const int grid = std::max(1, std::min(plan->sm_count, p.total_tiles));
     kern<<<grid, 512, S::total, stream>>>(p);
+    count_launch();
     TA_CUDA(cudaGetLastError());
     return TA_OK;
 }

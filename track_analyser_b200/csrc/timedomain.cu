@@ -452,6 +452,7 @@ int run_time_domain(const ta_plan* plan, const HostBatch& hb, const Workspace& w
 
     const int grid = std::max(1, std::min(hb.total_chunks, plan->sm_count * 8));
     time_domain_kernel<<<grid, TD_THREADS, 0, stream>>>(p);
+    count_launch();
     TA_CUDA(cudaGetLastError());
 
     FinParams f{};
@@ -468,6 +469,7 @@ int run_time_domain(const ta_plan* plan, const HostBatch& hb, const Workspace& w
     f.frame_m = plan->rms_m_frame; f.frame_s = plan->rms_s_frame;
     f.moments = out->moments;
     time_finalize_kernel<<<hb.n_tracks, 256, 0, stream>>>(f);
+    count_launch();
     TA_CUDA(cudaGetLastError());
     return TA_OK;
 }

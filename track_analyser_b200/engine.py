@@ -204,6 +204,20 @@ def run_device(plan: Plan, batch: DeviceBatch, bufs: FrontendBuffers, stage: str
     nat.check(fn(plan._h, C.byref(batch.c_batch), C.byref(bufs.c_out), C.c_void_p(ws.data_ptr()), ws.numel(), stream))
 
 
+def run_device_profiled(plan: Plan, batch: DeviceBatch, bufs: FrontendBuffers) -> list[float]:
+    """Fused frontend with per-stage device times (ms): [stft+mel+features, onset, autocorr, time-domain]."""
+    ws = workspace(plan, batch)
+    stream = C.c_void_p(torch.cuda.current_stream(batch.pcm.device).cuda_stream)
+    ms = (C.c_float * 4)()
+    nat.check(plan.lib.ta_frontend_run_profiled(plan._h, C.byref(batch.c_batch), C.byref(bufs.c_out),
+                                                C.c_void_p(ws.data_ptr()), ws.numel(), stream, ms))
+    return list(ms)
+
+
+def launch_count() -> int:
+    return int(nat.load().ta_launch_count())
+
+
 def download(batch: DeviceBatch, bufs: FrontendBuffers) -> list[TrackResult]:
     """Copy results to the host and cut them into per-track numpy arrays of reference shape."""
     plan = batch.plan
@@ -243,3 +257,86 @@ def analyse_batch(plan: Plan, tracks: Sequence[np.ndarray], outputs: Iterable[st
     bufs = FrontendBuffers(batch, outputs)
     run_device(plan, batch, bufs)
     return download(batch, bufs)
+
+
+class HostPipeline:
+    """Double-buffered host -> HBM -> host streaming of equal-length tracks.
+
+    The public end-to-end path for large batches: per chunk of ``chunk_tracks``
+    tracks it copies pinned host PCM to the device on a copy stream, runs the fused
+    frontend on a compute stream and copies every requested output back into
+    pinned host buffers on a third stream, so PCIe transfers in both directions
+    overlap the kernels of the neighbouring chunks.
+    """
+
+    def __init__(self, plan: Plan, n_samples: int, channels: int, chunk_tracks: int,
+                 outputs: Iterable[str] = ALL_OUTPUTS):
+        self.plan, self.n_samples, self.channels, self.chunk = plan, int(n_samples), int(channels), int(chunk_tracks)
+        dev = torch.device(f"cuda:{plan.device}")
+        self.stride = (channels * self.n_samples + 3) & ~3
+        offsets = np.arange(self.chunk, dtype=np.int64) * self.stride
+        ns = np.full(self.chunk, self.n_samples, dtype=np.int64)
+        self.dev_in = [torch.empty(self.chunk * self.stride, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.batches = [DeviceBatch(plan, d, offsets, ns, channels) for d in self.dev_in]
+        self.bufs = [FrontendBuffers(b, outputs) for b in self.batches]
+        self.host_out = [{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in bf.t.items()}
+                         for bf in self.bufs]
+        self.s_copy, self.s_comp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.ev_h2d = [torch.cuda.Event() for _ in range(2)]
+        self.ev_comp = [torch.cuda.Event() for _ in range(2)]
+        self.ev_d2h = [torch.cuda.Event() for _ in range(2)]
+        self.h2d_bytes_per_track = channels * self.n_samples * 4
+        self.d2h_bytes_per_chunk = self.bufs[0].bytes_d2h()
+        # partial final chunks reuse the full-size buffers with a shorter batch view
+        self._ws = workspace(plan, self.batches[0])
+
+    def run(self, host_tracks: Sequence[torch.Tensor], consume=None) -> int:
+        """Process ``host_tracks`` (pinned 1-d float32 tensors of C*N samples each).
+
+        ``consume(chunk_index, first_track, n_tracks, host_out_dict)`` is called once the
+        chunk's results are in pinned host memory.  Returns the number of chunks.
+        """
+        n = len(host_tracks)
+        n_chunks = (n + self.chunk - 1) // self.chunk
+        pending = [None, None]
+        cur = torch.cuda.current_stream()
+        for s in (self.s_copy, self.s_comp, self.s_out):
+            s.wait_stream(cur)
+
+        def finish(b):
+            if pending[b] is not None:
+                self.ev_d2h[b].synchronize()
+                if consume is not None:
+                    consume(*pending[b], self.host_out[b])
+                pending[b] = None
+
+        for ci in range(n_chunks):
+            b = ci & 1
+            finish(b)  # the host has consumed buffer b's previous results
+            first = ci * self.chunk
+            cnt = min(self.chunk, n - first)
+            with torch.cuda.stream(self.s_copy):
+                self.s_copy.wait_event(self.ev_comp[b])
+                for j in range(cnt):
+                    self.dev_in[b][j * self.stride: j * self.stride + host_tracks[first + j].numel()].copy_(
+                        host_tracks[first + j], non_blocking=True)
+                self.ev_h2d[b].record(self.s_copy)
+            with torch.cuda.stream(self.s_comp):
+                self.s_comp.wait_event(self.ev_h2d[b])
+                self.s_comp.wait_event(self.ev_d2h[b])
+                batch = self.batches[b]
+                if cnt != self.chunk:
+                    batch = DeviceBatch(self.plan, self.dev_in[b], batch.offsets[:cnt], batch.n_samples[:cnt], self.channels)
+                    self._tail = batch  # keep host metadata alive until the stream has consumed it
+                run_device(self.plan, batch, self.bufs[b])
+                self.ev_comp[b].record(self.s_comp)
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_comp[b])
+                for k, v in self.bufs[b].t.items():
+                    self.host_out[b][k].copy_(v, non_blocking=True)
+                self.ev_d2h[b].record(self.s_out)
+            pending[b] = (ci, first, cnt)
+        finish(n_chunks & 1)
+        finish((n_chunks + 1) & 1)
+        cur.wait_stream(self.s_out)
+        return n_chunks
