@@ -59,6 +59,7 @@ struct ta_plan {
     int* d_mel_len = nullptr;   // [n_mels]
     int* d_mel_woff = nullptr;  // [n_mels]
     float* d_mel_w = nullptr;   // [nnz]
+    int mel_nnz = 0;
     // host copies
     std::vector<float> h_window;
     std::vector<float> h_mel_dense;

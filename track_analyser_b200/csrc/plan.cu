@@ -168,6 +168,7 @@ static int plan_build(ta_plan* p) {
         if ((rc = upload(&p->d_mel_len, len))) return rc;
         if ((rc = upload(&p->d_mel_woff, woff))) return rc;
         if ((rc = upload(&p->d_mel_w, w))) return rc;
+        p->mel_nnz = int(w.size());
     }
 
     double coefs[12];

@@ -28,6 +28,7 @@ struct StftParams {
     int total_tiles;
     int hop;
     int n_mels;
+    int mel_nnz;
     float roll_percent;
     const float2* tw1;
     const float2* tw2;
@@ -47,6 +48,16 @@ struct StftParams {
     uint32_t* mel_max;    // [n_tracks]
 };
 
+// |X| = sqrt(re^2+im^2) through MUFU.SQRT (max rel. error 2^-22): two orders of magnitude below the
+// fp32 FFT's own rounding noise and 1e3 below the parity tolerance, at a quarter of __fsqrt_rn's cost.
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 __device__ __forceinline__ void group_barrier(int g, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
 }
@@ -63,8 +74,12 @@ struct StftSmem {
     static constexpr bool TW1_SMEM = (N != 4096);  // 4096: tile + exchange leave no room, read tw1 through L1/L2
     static constexpr size_t tw1_bytes = TW1_SMEM ? size_t(15) * C::M * 8 : 0;
     static constexpr size_t tw2_bytes = size_t(16) * C::Q * 8;
-    static constexpr size_t total = tile_bytes + ex_bytes + tw1_bytes + tw2_bytes;
+    static constexpr size_t fixed = tile_bytes + ex_bytes + tw1_bytes + tw2_bytes;
+    // + mel tables (runtime size): 3 ints per band, then the packed weights
+    static size_t total(int n_mels, int mel_nnz) { return fixed + ((size_t(3) * n_mels * 4 + size_t(mel_nnz) * 4 + 15) / 16) * 16; }
 };
+
+__device__ __forceinline__ size_t col_out(const TrackDesc& td, int t0, int f) { return size_t(td.pitch_off) + t0 + f; }
 
 template <int N, int TF, bool STEREO>
 __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) {
@@ -78,6 +93,8 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
     float2* ex_all = reinterpret_cast<float2*>(smem_raw + S::tile_bytes);
     float2* tw1s = reinterpret_cast<float2*>(smem_raw + S::tile_bytes + S::ex_bytes);
     float2* tw2s = reinterpret_cast<float2*>(smem_raw + S::tile_bytes + S::ex_bytes + S::tw1_bytes);
+    int* mel_tab = reinterpret_cast<int*>(smem_raw + S::fixed);  // [3][n_mels]: start, len, woff
+    float* mel_ws = reinterpret_cast<float*>(mel_tab + 3 * p.n_mels);
 
     const int tid = threadIdx.x;
     const int g = tid / M, r = tid % M;
@@ -88,6 +105,14 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
         for (int i = tid; i < 15 * M; i += S::THREADS) tw1s[i] = p.tw1[i];
     const float2* tw1 = S::TW1_SMEM ? tw1s : p.tw1;
     for (int i = tid; i < 16 * C::Q; i += S::THREADS) tw2s[i] = p.tw2[i];
+    if (p.mel) {
+        for (int i = tid; i < p.n_mels; i += S::THREADS) {
+            mel_tab[i] = p.mel_start[i];
+            mel_tab[p.n_mels + i] = p.mel_len[i];
+            mel_tab[2 * p.n_mels + i] = p.mel_woff[i];
+        }
+        for (int i = tid; i < p.mel_nnz; i += S::THREADS) mel_ws[i] = p.mel_w[i];
+    }
     // window, pre-scaled: 1/2 for the Hermitian split, another 1/2 for (L+-R)/2
     float wreg[16];
 #pragma unroll
@@ -142,6 +167,13 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
             const int f = STEREO ? s : 2 * s;        // frame slot in tile
             const int t = t0 + f;                    // absolute frame
             const long long base = (long long)t * p.hop - N / 2;
+            {   // L2 prefetch of the samples this group's next frame adds (its last NG*hop samples)
+                const long long nb = base + N + (long long)r * 32;  // one 128-byte line per thread
+                if (r * 32 < NG * p.hop * (STEREO ? 1 : 2) && nb + 32 <= td.n_samples) {
+                    prefetch_l2(td.ch0 + nb);
+                    if (STEREO) prefetch_l2(td.ch1 + nb);
+                }
+            }
             float2 v[16];
             if (STEREO) {
                 const float* __restrict__ L = td.ch0;
@@ -198,14 +230,14 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
                 split_pair(ex[k], ex[(N - k) & (N - 1)], xa, xb);
                 const float pa = fmaf(xa.x, xa.x, xa.y * xa.y);
                 const float pb = fmaf(xb.x, xb.x, xb.y * xb.y);
-                const float ma = __fsqrt_rn(pa);
+                const float ma = fast_sqrt(pa);
                 tile[k * TFP + f] = ma;
                 if (STEREO) {
                     acc_l[i] += ma;
                     acc_m[i] += ma * ma;
                     acc_s[i] += pb;
                 } else {
-                    const float mb = __fsqrt_rn(pb);
+                    const float mb = fast_sqrt(pb);
                     if (second_ok) {
                         tile[k * TFP + f + 1] = mb;
                         acc_l[i] += ma + mb;
@@ -224,7 +256,6 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
         constexpr int RPW = 32 / TF;           // tile rows covered by one warp instruction
         const int f = lane % TF, sub = lane / TF;
         const bool fok = f < nf;
-        const size_t col = size_t(td.pitch_off) + t0 + f;  // column inside a packed per-frame series
         // (a) magnitude rows -> global, TF contiguous floats per row
         if (p.mag) {
             float* dst = p.mag + size_t(td.pitch_off) * B + t0 + f;
@@ -236,13 +267,23 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
             float* dst = p.mel + size_t(td.pitch_off) * p.n_mels + t0 + f;
             float vmax = 0.f;
             for (int m = warp * RPW + sub; m < p.n_mels; m += 16 * RPW) {
-                const int ks = p.mel_start[m], len = p.mel_len[m];
-                const float* __restrict__ wt = p.mel_w + p.mel_woff[m];
-                float acc = 0.f;
-                for (int j = 0; j < len; ++j) {
-                    const float a = tile[(ks + j) * TFP + f];
-                    acc = fmaf(__ldg(wt + j), a * a, acc);
+                const int ks = mel_tab[m], len = mel_tab[p.n_mels + m];
+                const float* wt = mel_ws + mel_tab[2 * p.n_mels + m];
+                const float* col = tile + ks * TFP + f;
+                float a0 = 0.f, a1 = 0.f;
+                int j = 0;
+                for (; j + 4 <= len; j += 4) {
+                    const float x0 = col[(j + 0) * TFP], x1 = col[(j + 1) * TFP], x2 = col[(j + 2) * TFP], x3 = col[(j + 3) * TFP];
+                    a0 = fmaf(wt[j + 0], x0 * x0, a0);
+                    a1 = fmaf(wt[j + 1], x1 * x1, a1);
+                    a0 = fmaf(wt[j + 2], x2 * x2, a0);
+                    a1 = fmaf(wt[j + 3], x3 * x3, a1);
                 }
+                for (; j < len; ++j) {
+                    const float x0 = col[j * TFP];
+                    a0 = fmaf(wt[j], x0 * x0, a0);
+                }
+                const float acc = a0 + a1;
                 if (fok) {
                     dst[size_t(m) * td.ld] = acc;
                     vmax = fmaxf(vmax, acc);
@@ -254,57 +295,59 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
                 if (lane == 0) atomicMax(&p.mel_max[trk], __float_as_uint(vmax));
             }
         }
-        // (c) per-frame centroid / roll-off; bins split into 16*RPW chunks
+        // (c) per-frame centroid / roll-off; bins split into 16*RPW chunks.  Per chunk: fp32 partial sums
+        // s1 = sum |X| and s2 = sum (k-kb)|X| (<= 65 terms each), combined across chunks in double:
+        // centroid = df * sum_c (s2_c + kb_c*s1_c) / sum_c s1_c.  (librosa rounds |X|/sum to float32 before
+        // the float64 dot product; that changes the result by ~2e-9 relative, far inside rtol 1e-4.)
         if (p.centroid || p.rolloff_bin) {
             constexpr int NCH = 16 * RPW;
             constexpr int CH = (B + NCH - 1) / NCH;
-            // scratch aliases the (idle) exchange buffers
-            float* part_f = reinterpret_cast<float*>(ex_all);            // [NCH][TF]
-            double* part_d = reinterpret_cast<double*>(part_f + NCH * TF);  // [NCH][TF]
-            int* roll_s = reinterpret_cast<int*>(part_d + NCH * TF);        // [TF]
+            float* part_1 = reinterpret_cast<float*>(ex_all);   // [NCH][TF]  (aliases the idle exchange buffers)
+            float* part_2 = part_1 + NCH * TF;                  // [NCH][TF]
+            int* roll_s = reinterpret_cast<int*>(part_2 + NCH * TF);  // [TF]
             const int c = warp * RPW + sub;
             const int kb = c * CH, ke = min(kb + CH, B);
-            float sf = 0.f;
-            double sd = 0.0;
+            const float* col = tile + f;
+            float s1 = 0.f, s2 = 0.f;
             for (int k = kb; k < ke; ++k) {
-                const float a = tile[k * TFP + f];
-                sf += a;
-                sd += double(a);
+                const float a = col[k * TFP];
+                s1 += a;
+                s2 = fmaf(float(k - kb), a, s2);
             }
-            part_f[c * TF + f] = sf;
-            part_d[c * TF + f] = sd;
+            part_1[c * TF + f] = s1;
+            part_2[c * TF + f] = s2;
             if (tid < TF) roll_s[tid] = B;
             __syncthreads();
             float prefix = 0.f, total_f = 0.f;
-            double total_d = 0.0;
             for (int cc = 0; cc < NCH; ++cc) {
-                const float pf = part_f[cc * TF + f];
+                const float pf = part_1[cc * TF + f];
                 if (cc < c) prefix += pf;
                 total_f += pf;
-                total_d += part_d[cc * TF + f];
             }
             const float thr = p.roll_percent * total_f;
-            const double len = (total_d < 1.1754943508222875e-38) ? 1.0 : total_d;
-            double cen = 0.0;
-            float run = prefix;
             int first = B;
-            for (int k = kb; k < ke; ++k) {
-                const float a = tile[k * TFP + f];
-                run += a;
-                if (first == B && !(run < thr)) first = k;
-                const float an = float(double(a) / len);
-                cen = fma(p.freqs[k], double(an), cen);
+            if (c > 0 && !(prefix < thr)) {
+                first = kb;  // the crossing happened in an earlier chunk
+            } else {
+                float run = prefix;
+                for (int k = kb; k < ke; ++k) {
+                    run += col[k * TFP];
+                    if (!(run < thr)) { first = k; break; }
+                }
             }
             if (first < B) atomicMin(&roll_s[f], first);
-            __syncthreads();
-            part_d[c * TF + f] = cen;
-            __syncthreads();
-            if (c == 0 && fok) {
-                double tot = 0.0;
-                for (int cc = 0; cc < NCH; ++cc) tot += part_d[cc * TF + f];
-                if (p.centroid) p.centroid[col] = tot;
-                if (p.rolloff_bin) p.rolloff_bin[col] = roll_s[f];
+            if (c == 0 && fok && p.centroid) {
+                double num = 0.0, den = 0.0;
+                for (int cc = 0; cc < NCH; ++cc) {
+                    const double a1 = double(part_1[cc * TF + f]);
+                    den += a1;
+                    num += double(part_2[cc * TF + f]) + double(cc * CH) * a1;
+                }
+                const double df = p.freqs[1];
+                p.centroid[col_out(td, t0, f)] = (den < 1.1754943508222875e-38) ? df * num : df * num / den;
             }
+            __syncthreads();
+            if (c == 0 && fok && p.rolloff_bin) p.rolloff_bin[col_out(td, t0, f)] = roll_s[f];
         }
         __syncthreads();
     }
@@ -315,14 +358,14 @@ template <int N, int TF, bool STEREO>
 static int launch_stft(const ta_plan* plan, const StftParams& p, cudaStream_t stream) {
     using S = StftSmem<N, TF, STEREO>;
     auto kern = stft_fused_kernel<N, TF, STEREO>;
-    static bool configured[16] = {false};
-    int dev = plan->desc.device;
-    if (dev < 16 && !configured[dev]) {
-        TA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::total));
-        configured[dev] = true;
+    const size_t smem = S::total(p.n_mels, p.mel_nnz);
+    if (smem > 232448) {
+        set_error("mel tables do not fit in shared memory next to the STFT tile");
+        return TA_ERR_UNSUPPORTED;
     }
+    TA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::max(1, std::min(plan->sm_count, p.total_tiles));
-    kern<<<grid, 512, S::total, stream>>>(p);
+    kern<<<grid, 512, smem, stream>>>(p);
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TA_OK;
@@ -338,6 +381,7 @@ int run_stft_features(const ta_plan* plan, const HostBatch& hb, const Workspace&
     p.total_tiles = hb.total_tiles;
     p.hop = plan->desc.hop;
     p.n_mels = plan->desc.n_mels;
+    p.mel_nnz = plan->mel_nnz;
     p.roll_percent = float(plan->desc.roll_percent);
     p.tw1 = plan->d_tw1;
     p.tw2 = plan->d_tw2;

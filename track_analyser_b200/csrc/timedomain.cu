@@ -27,7 +27,9 @@ namespace ta {
 static constexpr int TD_THREADS = 256;
 static constexpr int TD_SEG = 8;                       // samples per thread per iteration
 static constexpr int TD_ITER = TD_THREADS * TD_SEG;    // 2048 samples per iteration
-static constexpr int TD_HALO = 8192;
+#ifndef TD_MIN_BLOCKS
+#define TD_MIN_BLOCKS 2
+#endif
 static constexpr int TD_MAXG = 1024;                   // granule accumulators per set per CTA
 
 struct Mat2 {
@@ -46,6 +48,7 @@ struct TdParams {
     int n_tracks;
     int total_chunks;
     int cs;        // chunk samples (multiple of TD_ITER)
+    int halo;      // warm-up samples before each chunk (multiple of TD_ITER)
     int stereo;
     int g_k, g_m, g_s;            // granule sizes: K-weighted, momentary hop, short-term hop
     int pitch_k, pitch_m, pitch_s;
@@ -66,18 +69,28 @@ __device__ __forceinline__ void matvec_add(const Mat2& M, double x0, double x1, 
     y1 = fma(M.m10, x0, fma(M.m11, x1, y1));
 }
 
+// Stage constants as laid out in shared memory (copied once per CTA: reading the by-value kernel
+// parameter block through LDC at ~70 distinct addresses thrashed the constant cache -- profiles/r1).
+struct StageSm {
+    double b0, b1, b2, a1, a2, pad;
+    Mat2 P[5];
+    Mat2 W;
+    double al[4][32];  // A^(8*lane), one row per matrix element: conflict-free lane-indexed reads
+};
+
 // One biquad stage over the thread's TD_SEG samples; x is replaced by the filter output (double).
 // carry0/carry1: filter state at the start of this iteration (updated to the state at its end).
-__device__ __forceinline__ void biquad_stage(const StageConst& c, const Mat2& al, double (&x)[TD_SEG], double& carry0,
+__device__ __forceinline__ void biquad_stage(const StageSm& c, double (&x)[TD_SEG], double& carry0,
                                              double& carry1, double2* wt /* [8] warp totals */, int lane, int warp) {
     // 1. zero-state response
+    const double b0 = c.b0, b1 = c.b1, b2 = c.b2, na1 = -c.a1, na2 = -c.a2;
     double z0 = 0.0, z1 = 0.0;
 #pragma unroll
     for (int i = 0; i < TD_SEG; ++i) {
         const double xi = x[i];
-        const double y = fma(c.b0, xi, z0);
-        z0 = fma(c.b1, xi, z1) - c.a1 * y;
-        z1 = c.b2 * xi - c.a2 * y;
+        const double y = fma(b0, xi, z0);
+        z0 = fma(na1, y, fma(b1, xi, z1));
+        z1 = fma(na2, y, b2 * xi);
         x[i] = y;
     }
     // 2. inclusive scan of end states inside the warp
@@ -108,21 +121,63 @@ __device__ __forceinline__ void biquad_stage(const StageConst& c, const Mat2& al
     double i0 = __shfl_up_sync(0xffffffffu, e0, 1);
     double i1 = __shfl_up_sync(0xffffffffu, e1, 1);
     if (lane == 0) { i0 = 0.0; i1 = 0.0; }
-    matvec_add(al, w0, w1, i0, i1);
+    {
+        const Mat2 al{c.al[0][lane], c.al[1][lane], c.al[2][lane], c.al[3][lane]};
+        matvec_add(al, w0, w1, i0, i1);
+    }
     // 5. add the zero-input response
 #pragma unroll
     for (int i = 0; i < TD_SEG; ++i) {
         const double yi = i0;
         x[i] += yi;
-        i0 = i1 - c.a1 * yi;
-        i1 = -c.a2 * yi;
+        i0 = fma(na1, yi, i1);
+        i1 = na2 * yi;
     }
 }
 
-// Adds `v` (sample index n) style partial sums into per-CTA granule accumulators.
-__device__ __forceinline__ void granule_add(double* acc, int first_gid, unsigned g, unsigned n_first, const float (&q)[TD_SEG],
-                                            const bool (&ok)[TD_SEG], int lane) {
-    const unsigned gid = n_first / g;
+// n / g for n < 2^31 without the ~20-instruction integer divide: double reciprocal + one correction.
+__device__ __forceinline__ unsigned fast_div(unsigned n, unsigned g, double inv_g) {
+    unsigned q = unsigned(double(n) * inv_g);
+    if (q * g > n) --q;
+    else if ((q + 1) * g <= n) ++q;
+    return q;
+}
+
+// Running granule sum kept in registers: all lanes of a warp sit in the same granule most of the
+// time, so each thread adds its 8 values locally and the warp reduces + publishes (one shared-memory
+// atomic) only when its granule changes.
+struct GranAcc {
+    double acc = 0.0;
+    unsigned gid = 0xffffffffu;
+};
+
+__device__ __forceinline__ void gran_flush(GranAcc& a, double* sm_acc, int first_gid, int lane) {
+    if (a.gid == 0xffffffffu) return;  // warp-uniform
+    double v = a.acc;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) atomicAdd(&sm_acc[int(a.gid) - first_gid], v);
+    a.acc = 0.0;
+    a.gid = 0xffffffffu;
+}
+
+// Adds the thread's TD_SEG values q[] (sample indices n_first..n_first+7).  `all_ok`: every sample of
+// the warp is inside the chunk (warp-uniform).
+__device__ __forceinline__ void granule_add(GranAcc& a, double* sm_acc, int first_gid, unsigned g, double inv_g, unsigned n_first,
+                                            const float (&q)[TD_SEG], const bool (&ok)[TD_SEG], bool all_ok, int lane) {
+    const unsigned n_warp = n_first - unsigned(lane) * TD_SEG;  // first sample of this warp
+    const unsigned gid_w = fast_div(n_warp, g, inv_g);          // warp-uniform
+    if (all_ok && n_warp + 32 * TD_SEG <= (gid_w + 1) * g) {
+        if (gid_w != a.gid) {
+            gran_flush(a, sm_acc, first_gid, lane);
+            a.gid = gid_w;
+        }
+        a.acc += (double(q[0]) + double(q[1])) + (double(q[2]) + double(q[3])) +
+                 ((double(q[4]) + double(q[5])) + (double(q[6]) + double(q[7])));
+        return;
+    }
+    gran_flush(a, sm_acc, first_gid, lane);
+    const unsigned gid = fast_div(n_first, g, inv_g);
     const unsigned boundary = (gid + 1) * g;  // first sample index of the next granule
     double lo = 0.0, hi = 0.0;
     bool any = false;
@@ -133,26 +188,31 @@ __device__ __forceinline__ void granule_add(double* acc, int first_gid, unsigned
             if (n_first + i < boundary) lo += double(q[i]); else hi += double(q[i]);
         }
     }
-    const bool crosses = n_first + TD_SEG > boundary;
-    const unsigned gid0 = __shfl_sync(0xffffffffu, gid, 0);
-    const bool uniform = __all_sync(0xffffffffu, gid == gid0 && !crosses);
-    if (uniform) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) lo += __shfl_xor_sync(0xffffffffu, lo, o);
-        const bool warp_any = __any_sync(0xffffffffu, any);
-        if (lane == 0 && warp_any) atomicAdd(&acc[int(gid) - first_gid], lo);
-    } else if (any) {
-        atomicAdd(&acc[int(gid) - first_gid], lo);
-        if (crosses) atomicAdd(&acc[int(gid) + 1 - first_gid], hi);
+    if (any) {
+        atomicAdd(&sm_acc[int(gid) - first_gid], lo);
+        if (n_first + TD_SEG > boundary) atomicAdd(&sm_acc[int(gid) + 1 - first_gid], hi);
     }
 }
 
-__global__ void __launch_bounds__(TD_THREADS) time_domain_kernel(const __grid_constant__ TdParams p) {
+__global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(const __grid_constant__ TdParams p) {
     __shared__ double2 wt[2][TD_THREADS / 32];
     __shared__ double gacc[3][TD_MAXG];
     __shared__ double red[TD_THREADS / 32][7];
+    __shared__ StageSm cst[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const Mat2 al0 = p.stage[0].AL[lane], al1 = p.stage[1].AL[lane];  // lane-indexed once, then registers
+    if (tid < 2) {
+        const StageConst& c = p.stage[tid];
+        StageSm& d = cst[tid];
+        d.b0 = c.b0; d.b1 = c.b1; d.b2 = c.b2; d.a1 = c.a1; d.a2 = c.a2; d.pad = 0.0;
+        for (int i = 0; i < 5; ++i) d.P[i] = c.P[i];
+        d.W = c.W;
+    }
+    if (tid < 64) {  // lane-indexed powers: a divergent constant-bank read, done once per CTA
+        const Mat2 m = p.stage[tid >> 5].AL[tid & 31];
+        StageSm& d = cst[tid >> 5];
+        d.al[0][tid & 31] = m.m00; d.al[1][tid & 31] = m.m01; d.al[2][tid & 31] = m.m10; d.al[3][tid & 31] = m.m11;
+    }
+    __syncthreads();
 
     for (int w = blockIdx.x; w < p.total_chunks; w += gridDim.x) {
         // locate track
@@ -165,7 +225,7 @@ __global__ void __launch_bounds__(TD_THREADS) time_domain_kernel(const __grid_co
         const TrackDesc td = p.tracks[trk];
         const long long cs0 = (long long)(w - td.chunk_begin) * p.cs;
         const long long ce = min(cs0 + (long long)p.cs, (long long)td.n_samples);
-        const long long ws = max(0ll, cs0 - TD_HALO);
+        const long long ws = max(0ll, cs0 - (long long)p.halo);
         const int fg_k = int(cs0 / p.g_k), fg_m = int(cs0 / p.g_m), fg_s = int(cs0 / p.g_s);
         for (int i = tid; i < 3 * TD_MAXG; i += TD_THREADS) (&gacc[0][0])[i] = 0.0;
         __syncthreads();
@@ -174,6 +234,8 @@ __global__ void __launch_bounds__(TD_THREADS) time_domain_kernel(const __grid_co
         const float* __restrict__ R = td.ch1;
         const bool vec = ((reinterpret_cast<uintptr_t>(L) & 15) == 0) && (!p.stereo || (reinterpret_cast<uintptr_t>(R) & 15) == 0);
         double c10 = 0, c11 = 0, c20 = 0, c21 = 0;  // carries of stage 1 / stage 2
+        GranAcc ga_k, ga_m, ga_s;
+        const double inv_k = 1.0 / double(p.g_k), inv_m = 1.0 / double(p.g_m), inv_s = 1.0 / double(p.g_s);
         double sL = 0, sR = 0, sLL = 0, sRR = 0, sLR = 0, sMM = 0, sSS = 0;
 
         for (long long n0 = ws; n0 < ce; n0 += TD_ITER) {
@@ -196,46 +258,60 @@ __global__ void __launch_bounds__(TD_THREADS) time_domain_kernel(const __grid_co
                     r[i] = (in && p.stereo) ? __ldg(R + nf + i) : 0.f;
                 }
             }
-            float mono[TD_SEG];
+            // ---- raw-sample statistics first, so l/r/mono are dead before the filter stages ----
+            const bool warm = n0 + TD_ITER <= cs0;  // warm-up iteration: nothing is accumulated (CTA-uniform)
+            const long long nw = n0 + (long long)warp * 32 * TD_SEG;
+            const bool all_ok = nw >= cs0 && nw + 32 * TD_SEG <= ce;  // warp-uniform
+            const unsigned n32 = unsigned(nf);
             bool ok[TD_SEG];
             double x[TD_SEG];
+            {
+                float qm[TD_SEG];
 #pragma unroll
-            for (int i = 0; i < TD_SEG; ++i) {
-                mono[i] = p.stereo ? 0.5f * (l[i] + r[i]) : l[i];
-                ok[i] = (nf + i >= cs0) && (nf + i < ce);
-                x[i] = double(mono[i]);
-            }
-            // K-weighting: shelf, float32 round trip, high-pass, float32 round trip
-            biquad_stage(p.stage[0], al0, x, c10, c11, wt[0], lane, warp);
+                for (int i = 0; i < TD_SEG; ++i) {
+                    const float mono = p.stereo ? 0.5f * (l[i] + r[i]) : l[i];
+                    ok[i] = all_ok || ((nf + i >= cs0) && (nf + i < ce));
+                    x[i] = double(mono);
+                    qm[i] = mono * mono;
+                }
+                if (!warm) {
 #pragma unroll
-            for (int i = 0; i < TD_SEG; ++i) x[i] = double(float(x[i]));
-            biquad_stage(p.stage[1], al1, x, c20, c21, wt[1], lane, warp);
-            float qk[TD_SEG], qm[TD_SEG];
-#pragma unroll
-            for (int i = 0; i < TD_SEG; ++i) {
-                const float y = float(x[i]);
-                qk[i] = y * y;
-                qm[i] = mono[i] * mono[i];
-                if (ok[i]) {
-                    if (p.stereo) {
-                        const double dl = l[i], dr = r[i];
-                        const float sd = 0.5f * (l[i] - r[i]);
-                        sL += dl; sR += dr; sLL += dl * dl; sRR += dr * dr; sLR += dl * dr;
-                        sSS += double(sd) * double(sd);
-                    } else {
-                        sL += double(l[i]);
-                        sLL += double(l[i]) * double(l[i]);
+                    for (int i = 0; i < TD_SEG; ++i) {
+                        if (!all_ok && !ok[i]) continue;
+                        const double dm = x[i], dl = l[i];
+                        sMM = fma(dm, dm, sMM);
+                        sL += dl;
+                        sLL = fma(dl, dl, sLL);
+                        if (p.stereo) {
+                            const double dr = r[i], sd = double(0.5f * (l[i] - r[i]));
+                            sR += dr;
+                            sRR = fma(dr, dr, sRR);
+                            sLR = fma(dl, dr, sLR);
+                            sSS = fma(sd, sd, sSS);
+                        }
                     }
-                    sMM += double(mono[i]) * double(mono[i]);
+                    if (p.gran_m) granule_add(ga_m, gacc[1], fg_m, unsigned(p.g_m), inv_m, n32, qm, ok, all_ok, lane);
+                    if (p.gran_s) granule_add(ga_s, gacc[2], fg_s, unsigned(p.g_s), inv_s, n32, qm, ok, all_ok, lane);
                 }
             }
-            {
-                const unsigned n32 = unsigned(nf);
-                if (p.gran_k) granule_add(gacc[0], fg_k, unsigned(p.g_k), n32, qk, ok, lane);
-                if (p.gran_m) granule_add(gacc[1], fg_m, unsigned(p.g_m), n32, qm, ok, lane);
-                if (p.gran_s) granule_add(gacc[2], fg_s, unsigned(p.g_s), n32, qm, ok, lane);
+            // ---- K-weighting: shelf, float32 round trip, high-pass, float32 round trip ----
+            biquad_stage(cst[0], x, c10, c11, wt[0], lane, warp);
+#pragma unroll
+            for (int i = 0; i < TD_SEG; ++i) x[i] = double(float(x[i]));
+            biquad_stage(cst[1], x, c20, c21, wt[1], lane, warp);
+            if (!warm && p.gran_k) {
+                float qk[TD_SEG];
+#pragma unroll
+                for (int i = 0; i < TD_SEG; ++i) {
+                    const float y = float(x[i]);
+                    qk[i] = y * y;
+                }
+                granule_add(ga_k, gacc[0], fg_k, unsigned(p.g_k), inv_k, n32, qk, ok, all_ok, lane);
             }
         }
+        gran_flush(ga_k, gacc[0], fg_k, lane);
+        gran_flush(ga_m, gacc[1], fg_m, lane);
+        gran_flush(ga_s, gacc[2], fg_s, lane);
         __syncthreads();
         // flush granules (a granule is shared by at most two chunks -> a + b is order independent)
         const int ng_k = int((ce - 1) / p.g_k) - fg_k + 1, ng_m = int((ce - 1) / p.g_m) - fg_m + 1,
@@ -447,6 +523,14 @@ int run_time_domain(const ta_plan* plan, const HostBatch& hb, const Workspace& w
     TA_CUDA(cudaMemsetAsync(ws.d_granules, 0, sizeof(double) * need, stream));
     if (p.moments) TA_CUDA(cudaMemsetAsync(p.moments, 0, sizeof(double) * 8 * hb.n_tracks, stream));
 
+    // warm-up length: the slowest K-weighting pole pair is the high-pass double pole of radius r = sqrt(a2);
+    // a zero-input response decays like n*r^n, so take the first multiple of TD_ITER with n*r^n < 1e-10.
+    {
+        const double r = std::sqrt(std::fabs(plan->highpass.a2));
+        int n = TD_ITER;
+        while (n < (1 << 22) && double(n) * std::pow(r, double(n)) > 1e-10) n += TD_ITER;
+        p.halo = n;
+    }
     p.stage[0] = make_stage(plan->shelf);
     p.stage[1] = make_stage(plan->highpass);
 

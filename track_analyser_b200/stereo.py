@@ -75,11 +75,19 @@ def correlation_from_moments(m) -> float:
     return float(np.clip((m[4] - m[0] * m[1] / n) / denom, -1.0, 1.0))
 
 
-def width_from_band_energy(band_energy, freqs, n_frames, bands, sample_rate) -> dict[str, float]:
+def width_from_band_energy(band_energy, freqs, n_frames, bands, sample_rate, moments=None) -> dict[str, float]:
+    """Band-wise sqrt(mean |S|^2 / mean |M|^2) from the per-bin time sums of the STFT kernel.
+
+    If the time-domain side signal is identically zero (``moments[6] == 0``: L == R sample for
+    sample) its STFT is identically zero too, and the reference returns exactly 0.0
+    (tests/test_stereo.py:15-27); the packed fp32 FFT would instead leave rounding noise of the
+    mid channel in the side spectrum, so that case is answered exactly here."""
     nyq = sample_rate / 2.0
     if bands is None:
         bands = (("low", 0.0, min(200.0, nyq)), ("mid", 200.0, min(2_000.0, nyq)), ("high", 2_000.0, nyq))
     out = {"low": 0.0, "mid": 0.0, "high": 0.0}
+    if moments is not None and float(moments[6]) == 0.0:
+        return out
     for name, lo, hi in bands:
         sel = (freqs >= lo) & (freqs <= hi)
         if not np.any(sel):
@@ -115,9 +123,9 @@ def frequency_dependent_width(stereo: np.ndarray, sample_rate: int, *,
                               bands: Sequence[tuple[str, float, float]] | None = None, n_fft: int = 2_048,
                               hop_length: int = 512) -> StereoWidthBands:
     st = _as_pair(stereo)
-    res = runtime.frontend(st, sample_rate, n_fft=n_fft, hop=hop_length, outputs=("band_energy",))
+    res = runtime.frontend(st, sample_rate, n_fft=n_fft, hop=hop_length, outputs=("band_energy", "moments"))
     freqs = np.fft.rfftfreq(n=n_fft, d=1.0 / sample_rate)
-    w = width_from_band_energy(res["band_energy"], freqs, res.n_frames, bands, sample_rate)
+    w = width_from_band_energy(res["band_energy"], freqs, res.n_frames, bands, sample_rate, res["moments"])
     return StereoWidthBands(low=w.get("low", 0.0), mid=w.get("mid", 0.0), high=w.get("high", 0.0))
 
 
