@@ -116,6 +116,10 @@ typedef struct ta_frontend_out {
     double* lufs;          /* [n_tracks] gated integrated loudness: loudness.py:61 */
     double* rms_momentary; /* [n_tracks * rms_pitch] mean-square of centred frames, 0.4 s window: loudness.py:57 */
     double* rms_short;     /* [n_tracks * rms_pitch] same, 3.0 s window: loudness.py:56 */
+    float* frame_max;      /* [P]      max_f |X| per frame (input of the tuning estimate) */
+    float* chroma;         /* [12 * P] chroma_stft, inf-normalised per frame: harmony.py:108,149 (needs magnitude) */
+    double* tuning;        /* [n_tracks] estimated tuning in fractions of a bin (librosa.estimate_tuning) */
+    float* tempogram;      /* [win * P] autocorrelation tempogram of onset_env: report.py:260 */
     int32_t kw_pitch;      /* capacity per track of kw_blocks */
     int32_t rms_pitch;     /* capacity per track of rms_momentary / rms_short */
 } ta_frontend_out;
@@ -162,6 +166,17 @@ TA_API int ta_autocorrelate(const ta_plan* plan, const ta_batch* batch, const fl
  * mid/side/LR moments and the centred RMS frames: loudness.py:30-61,118; stereo.py:62-83. */
 TA_API int ta_time_domain(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out,
                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* K2b: chroma_stft on an existing magnitude spectrogram: tuning estimate (piptrack on the power
+ * spectrogram, median gate, 0.01-bin histogram), chroma filterbank for that tuning, projection and
+ * per-frame inf-norm: librosa.feature.chroma_stft at harmony.py:108,149. */
+TA_API int ta_chroma_stft(const ta_plan* plan, const ta_batch* batch, const float* magnitude, const float* frame_max,
+                          float* chroma, double* tuning, void* workspace, size_t workspace_bytes, void* stream);
+
+/* K4b: windowed (tempogram_win frames, Hann, centred, inf-normalised) autocorrelation of the onset
+ * envelope: librosa.feature.tempogram at report.py:260.  Output rows = lags, (win, T_i) per track. */
+TA_API int ta_tempogram(const ta_plan* plan, const ta_batch* batch, const float* onset_env, float* tempogram,
+                        void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -298,3 +298,89 @@ def test_abi_errors():
     assert rc == nat.TA_ERR_INVALID
     with pytest.raises(ValueError):
         engine.upload(plan, [x, x[0]])
+
+
+# ------------------------------------------------------------------------------ chroma_stft / tempogram (K2b, K4b)
+@pytest.mark.parametrize("sr,seconds,channels", [(44_100, 8.0, 2), (48_000, 5.0, 1), (22_050, 6.0, 1)])
+def test_chroma_stft_and_tuning_match_oracle(sr, seconds, channels):
+    x = synth.synth_track(21, seconds, sr, channels)
+    mono = np.mean(x, axis=0) if x.ndim == 2 else x
+    r = engine.analyse_batch(plan_for(sr), [x], ("chroma", "tuning"))[0]
+    ref, tuning = olr.chroma_stft(mono, sr, return_tuning=True)
+    assert r["tuning"] == pytest.approx(tuning, abs=1e-12)  # histogram arg-max: an integer decision, must be exact
+    assert r["chroma"].shape == ref.shape
+    np.testing.assert_allclose(r["chroma"], ref, rtol=RTOL, atol=2e-6)
+
+
+def test_chroma_of_detuned_tone_and_silence():
+    sr = 44_100
+    t = np.arange(4 * sr) / sr
+    x = (0.4 * np.sin(2 * np.pi * 446.0 * t) + 0.2 * np.sin(2 * np.pi * 892.0 * t)).astype(np.float32)  # A4 + 23 cents
+    r = engine.analyse_batch(plan_for(sr), [x, np.zeros(sr, np.float32)], ("chroma", "tuning"))
+    ref, tuning = olr.chroma_stft(x, sr, return_tuning=True)
+    assert r[0]["tuning"] == pytest.approx(tuning, abs=1e-12) and abs(tuning) > 0.05
+    np.testing.assert_allclose(r[0]["chroma"], ref, rtol=RTOL, atol=2e-6)
+    assert r[1]["tuning"] == 0.0 and np.all(r[1]["chroma"] == 0.0)  # librosa: no pitches -> tuning 0, zero frames stay zero
+
+
+@pytest.mark.parametrize("sr,seconds", [(44_100, 12.0), (48_000, 3.0)])
+def test_tempogram_matches_oracle(sr, seconds):
+    x = synth.synth_track(31, seconds, sr, 1)
+    r = engine.analyse_batch(plan_for(sr), [x], ("onset_env", "tempogram"))[0]
+    env = olr.onset_strength(y=x, sr=sr, hop_length=512)
+    ref = olr.tempogram(onset_envelope=env, sr=sr, hop_length=512)
+    assert r["tempogram"].shape == ref.shape == (384, r.n_frames)
+    # normalised autocorrelation in [-1, 1]: fp32 transform noise is ~1e-6 absolute
+    np.testing.assert_allclose(r["tempogram"], ref, rtol=RTOL, atol=5e-6)
+    np.testing.assert_allclose(r["tempogram"][0], np.where(np.abs(ref[0]) > 0, 1.0, 0.0), atol=1e-6)  # lag 0 is the max
+
+
+def test_tempogram_short_track_inside_window():
+    sr = 44_100
+    g = np.load(os.path.join(GOLDEN, "tiny_click.npz"))  # T = 175 < 384
+    r = engine.analyse_batch(plan_for(sr), [g["samples"]], ("tempogram",))[0]
+    env = olr.onset_strength(y=g["samples"], sr=sr, hop_length=512)
+    np.testing.assert_allclose(r["tempogram"], olr.tempogram(onset_envelope=env, sr=sr), rtol=RTOL, atol=5e-6)
+
+
+# ------------------------------------------------------------------------------ analyse_track
+def test_analyse_track_pipeline_like_reference():
+    from track_analyser_b200 import harmony, pipeline
+    from track_analyser_b200.utils import AudioInput
+
+    sr = 44_100
+    x = synth.synth_track(synth.DEFAULT_SEED, 20.0, sr, 2)
+    mono = np.mean(x, axis=0)
+    audio = AudioInput(samples=mono, sample_rate=sr, stereo_samples=x)
+    stages = []
+    before = engine.launch_count()
+    res = pipeline.analyse_track(audio, progress_callback=stages.append)
+    launches = engine.launch_count() - before
+    assert stages == ["audio", "beats", "structure", "loudness", "harmonic", "features", "stereo"]  # pipeline.py:58-118
+    assert 90.0 <= res.beat.bpm <= 135.0 and len(res.beat.beat_frames) == len(res.beat.beat_times)
+    # integer outputs against the oracle-driven host logic
+    env = ofe.onset_envelope(mono, sr)
+    bpm = ptempo._bpm_from_autocorr(env, ofe.onset_autocorrelation(env), sr, 90.0, 135.0, 512)
+    assert res.beat.bpm == pytest.approx(bpm, rel=1e-9)
+    o_mag, o_mel, o_logmel, o_flux = ofe.structure_frontend(mono, sr)
+    assert pass_rate(res.structure.magnitude, o_mag) >= 0.99999
+    np.testing.assert_allclose(res.structure.spectral_flux, o_flux, rtol=RTOL, atol=ATOL * float(o_mel.max()))
+    np.testing.assert_allclose(res.structure.log_mel, o_logmel, rtol=RTOL, atol=1e-3)
+    lo, mid, hi = ofe.spectral_balance(mono, sr)
+    sb = res.harmonic.spectral_balance
+    assert (sb.low_band, sb.mid_band, sb.high_band) == pytest.approx((lo, mid, hi), rel=RTOL)
+    ref_chroma, ref_tuning = ofe.chroma_stft(mono, sr, return_tuning=True)
+    assert res.harmonic.tuning == pytest.approx(ref_tuning, abs=1e-12)
+    np.testing.assert_allclose(res.harmonic.chroma_stft, ref_chroma, rtol=RTOL, atol=2e-6)
+    # key index (integer output) from GPU chroma == from oracle chroma
+    k_gpu = harmony.key_index(harmony._rank_keys(*harmony._score_keys([res.harmonic.chroma_stft])))
+    k_ref = harmony.key_index(harmony._rank_keys(*harmony._score_keys([ref_chroma])))
+    assert k_gpu == k_ref
+    assert res.loudness.integrated_lufs == pytest.approx(opl.integrated_loudness(mono, sr), abs=0.01)
+    assert res.features.ltas.magnitude.shape == (1025,)
+    m, s = ofe.mid_side_rms(x)
+    assert (res.stereo.mid_rms, res.stereo.side_rms) == pytest.approx((m, s), rel=RTOL)
+    # the >= 11 identical STFT requests of the reference collapse: two fused runs (2048/512 and 4096/1024)
+    assert 0 < launches <= 60
+    with pytest.raises(TypeError):
+        harmony.harmony_frontend("not audio")

@@ -73,6 +73,10 @@ class FrontendOut(C.Structure):
         ("lufs", C.c_void_p),
         ("rms_momentary", C.c_void_p),
         ("rms_short", C.c_void_p),
+        ("frame_max", C.c_void_p),
+        ("chroma", C.c_void_p),
+        ("tuning", C.c_void_p),
+        ("tempogram", C.c_void_p),
         ("kw_pitch", C.c_int32),
         ("rms_pitch", C.c_int32),
     ]
@@ -93,6 +97,8 @@ SYMBOLS = {
     "ta_stft_features": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(FrontendOut), C.c_void_p, C.c_size_t, C.c_void_p]),
     "ta_onset_flux": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ta_autocorrelate": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ta_chroma_stft": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ta_tempogram": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ta_time_domain": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(FrontendOut), C.c_void_p, C.c_size_t, C.c_void_p]),
 }
 

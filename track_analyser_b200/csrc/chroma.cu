@@ -1,0 +1,301 @@
+// K2b: chroma_stft = tuning estimate + chroma filterbank + projection + per-frame inf-norm.
+//
+// Replaces librosa.feature.chroma_stft(y, sr) (norm=inf, tuning=None) as called from
+// harmony.py:108,149.  Stages, all per track and all on the device (no host round trip
+// for the data-dependent tuning):
+//   pip_peaks   librosa.piptrack on the POWER spectrogram S = |X|^2 (chroma_stft passes S):
+//               bins in [150 Hz, min(4000 Hz, sr/2)), local maxima of S*(S > 0.1*max_f S),
+//               parabolic shift, interpolated magnitude; peaks are appended to a per-track
+//               list (magnitude, 0.01-semitone histogram bin of the tuning residual).
+//   tuning      estimate_tuning: median of the peak magnitudes by radix select on the float
+//               bit patterns, 100-bin histogram of the residuals of the peaks >= median,
+//               left edge of the arg-max bin.
+//   chroma_fb   librosa.filters.chroma(tuning): Gaussian bumps over log-frequency, per-column
+//               L2 normalisation, Gaussian octave weighting, roll by -3, float32.
+//   project     raw[c,t] = sum_f fb[c,f] * S[f,t], then divide each frame by its max.
+// The projection is HBM-bound (reads the magnitude once, 4*B*T bytes per track, 13 flop per
+// element) on CUDA cores; a tcgen05 version cannot beat an HBM-bound kernel and TF32 would
+// break the 1e-4 parity bar (DESIGN.md section "filterbank contraction").
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace ta {
+
+struct PeakList {
+    float* mag;            // [cap_total]
+    unsigned char* bin;    // [cap_total]
+    unsigned int* count;   // [n_tracks]
+    const size_t* offset;  // [n_tracks] start of each track's region
+};
+
+__device__ __forceinline__ int residual_bin(float pitch) {
+    // pitch_tuning: residual = mod(12*log2(f/27.5), 1), folded to [-0.5, 0.5); np.histogram over linspace(-0.5,0.5,101)
+    float res = 12.0f * log2f(pitch / 27.5f);
+    res = res - floorf(res);
+    if (res >= 0.5f) res -= 1.0f;
+    const double x = double(res);
+    int i = int(floor((x + 0.5) * 100.0));
+    i = max(0, min(99, i));
+    while (i > 0 && x < -0.5 + i * 0.01) --i;
+    while (i < 99 && x >= ((i + 1 == 100) ? 0.5 : -0.5 + (i + 1) * 0.01)) ++i;
+    return i;
+}
+
+__global__ void __launch_bounds__(256) pip_peaks_kernel(const TrackDesc* __restrict__ tracks, const float* __restrict__ mag,
+                                                       const float* __restrict__ frame_max, PeakList pl, int n_bins, int kmin,
+                                                       int kmax, float bin_hz) {
+    const TrackDesc td = tracks[blockIdx.y];
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= td.n_frames) return;
+    const float* __restrict__ col = mag + size_t(td.pitch_off) * n_bins + t;
+    const float mx = frame_max[td.pitch_off + t];
+    const float ref = 0.1f * (mx * mx);
+    float* out_mag = pl.mag + pl.offset[blockIdx.y];
+    unsigned char* out_bin = pl.bin + pl.offset[blockIdx.y];
+    auto S = [&](int k) {
+        const float m = col[size_t(k) * td.ld];
+        return m * m;
+    };
+    float sm = S(kmin - 1), s0 = S(kmin);
+    for (int k = kmin; k < kmax; ++k) {
+        const float sp = S(k + 1);
+        const float xm = sm > ref ? sm : 0.f, x0 = s0 > ref ? s0 : 0.f, xp = sp > ref ? sp : 0.f;
+        if (x0 > xm && x0 >= xp) {
+            // parabolic interpolation (float64 from float32 inputs, result stored as float32)
+            const double a = double(sp) + double(sm) - 2.0 * double(s0);
+            const double b = (double(sp) - double(sm)) / 2.0;
+            const float shift = (fabs(b) >= fabs(a)) ? 0.f : float(-b / a);
+            const float avg = (sp - sm) / 2.0f;
+            const float dskew = 0.5f * avg * shift;
+            const float pitch = float((double(k) + double(shift)) * double(bin_hz));
+            const float m = s0 + dskew;
+            if (pitch > 0.f) {
+                const unsigned slot = atomicAdd(&pl.count[blockIdx.y], 1u);
+                out_mag[slot] = m;
+                out_bin[slot] = (unsigned char)residual_bin(pitch);
+            }
+        }
+        sm = s0;
+        s0 = sp;
+    }
+}
+
+__device__ __forceinline__ unsigned ordered_key(float v) {
+    const unsigned b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(unsigned k) {
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+// k-th smallest (0-based) of n floats by 4 x 8-bit radix select; all threads of the CTA call this.
+__device__ float block_select(const float* __restrict__ v, unsigned n, unsigned k, unsigned* hist /* smem[256] */,
+                              unsigned* bcast /* smem[2] */) {
+    unsigned prefix = 0, mask = 0;
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+        __syncthreads();
+        for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+            const unsigned key = ordered_key(v[i]);
+            if ((key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned acc = 0, d = 0;
+            for (; d < 256; ++d) {
+                if (acc + hist[d] > k) break;
+                acc += hist[d];
+            }
+            bcast[0] = d;
+            bcast[1] = k - acc;
+        }
+        __syncthreads();
+        prefix |= bcast[0] << shift;
+        mask |= 0xffu << shift;
+        k = bcast[1];
+        __syncthreads();
+    }
+    return key_to_float(prefix);
+}
+
+__global__ void __launch_bounds__(1024) tuning_kernel(PeakList pl, double* __restrict__ tuning) {
+    __shared__ unsigned hist[256];
+    __shared__ unsigned bc[2];
+    __shared__ unsigned counts[100];
+    const int trk = blockIdx.x;
+    const unsigned n = pl.count[trk];
+    const float* v = pl.mag + pl.offset[trk];
+    const unsigned char* b = pl.bin + pl.offset[trk];
+    if (n == 0) {  // pitch_tuning on an empty set returns 0.0
+        if (threadIdx.x == 0) tuning[trk] = 0.0;
+        return;
+    }
+    const float lo = block_select(v, n, (n - 1) / 2, hist, bc);
+    const float hi = block_select(v, n, n / 2, hist, bc);
+    const float thr = __fadd_rn(lo, hi) * 0.5f;  // np.median of float32: mean of the two middle values
+    for (int i = threadIdx.x; i < 100; i += blockDim.x) counts[i] = 0;
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x)
+        if (v[i] >= thr) atomicAdd(&counts[b[i]], 1u);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int best = 0;
+        for (int i = 1; i < 100; ++i)
+            if (counts[i] > counts[best]) best = i;
+        tuning[trk] = -0.5 + best * 0.01;
+    }
+}
+
+// librosa.filters.chroma for one track; thread per FFT bin (column), 12 chroma rows.
+__global__ void __launch_bounds__(256) chroma_fb_kernel(const double* __restrict__ tuning, float* __restrict__ fb /* [trk][B][12] */,
+                                                       int n_bins, int n_fft, double sr) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_bins) return;
+    const int trk = blockIdx.y;
+    const double a440 = 440.0 * exp2(tuning[trk] / 12.0);
+    const double step = sr / double(n_fft);
+    auto frq = [&](int j) {  // frqbins[j]
+        if (j == 0) return 12.0 * log2((1.0 * step) / (a440 / 16.0)) - 18.0;
+        return 12.0 * log2((double(j) * step) / (a440 / 16.0));
+    };
+    const double fk = frq(k);
+    const double width = (k + 1 < n_fft) ? fmax(frq(k + 1) - fk, 1.0) : 1.0;
+    double w[12], ss = 0.0;
+#pragma unroll
+    for (int c = 0; c < 12; ++c) {
+        double D = fk - double(c) + 6.0 + 120.0;
+        D = D - 12.0 * floor(D / 12.0) - 6.0;  // np.remainder(., 12) - 6
+        const double z = 2.0 * D / width;
+        w[c] = exp(-0.5 * z * z);
+        ss += w[c] * w[c];
+    }
+    double len = sqrt(ss);
+    if (len < 2.2250738585072014e-308) len = 1.0;
+    const double oct = (fk / 12.0 - 5.0) / 2.0;
+    const double octw = exp(-0.5 * oct * oct);
+    float* dst = fb + (size_t(trk) * n_bins + k) * 12;
+#pragma unroll
+    for (int c = 0; c < 12; ++c) dst[c] = float((w[(c + 3) % 12] / len) * octw);  // roll(-3) then float32
+}
+
+__global__ void __launch_bounds__(256) chroma_project_kernel(const TrackDesc* __restrict__ tracks, const float* __restrict__ mag,
+                                                            const float* __restrict__ fb, float* __restrict__ out, int n_bins) {
+    constexpr int KC = 128;
+    __shared__ __align__(16) float wsm[KC * 12];
+    const TrackDesc td = tracks[blockIdx.y];
+    if (blockIdx.x * blockDim.x >= td.n_frames) return;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool ok = t < td.n_frames;
+    const float* __restrict__ col = mag + size_t(td.pitch_off) * n_bins + (ok ? t : 0);
+    const float* __restrict__ w = fb + size_t(blockIdx.y) * n_bins * 12;
+    float acc[12];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) acc[c] = 0.f;
+    for (int k0 = 0; k0 < n_bins; k0 += KC) {
+        const int kn = min(KC, n_bins - k0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < kn * 12; i += blockDim.x) wsm[i] = w[size_t(k0) * 12 + i];
+        __syncthreads();
+        for (int kk = 0; kk < kn; ++kk) {
+            const float m = col[size_t(k0 + kk) * td.ld];
+            const float s = m * m;
+            const float4 w0 = *reinterpret_cast<const float4*>(wsm + kk * 12);
+            const float4 w1 = *reinterpret_cast<const float4*>(wsm + kk * 12 + 4);
+            const float4 w2 = *reinterpret_cast<const float4*>(wsm + kk * 12 + 8);
+            acc[0] = fmaf(w0.x, s, acc[0]); acc[1] = fmaf(w0.y, s, acc[1]); acc[2] = fmaf(w0.z, s, acc[2]); acc[3] = fmaf(w0.w, s, acc[3]);
+            acc[4] = fmaf(w1.x, s, acc[4]); acc[5] = fmaf(w1.y, s, acc[5]); acc[6] = fmaf(w1.z, s, acc[6]); acc[7] = fmaf(w1.w, s, acc[7]);
+            acc[8] = fmaf(w2.x, s, acc[8]); acc[9] = fmaf(w2.y, s, acc[9]); acc[10] = fmaf(w2.z, s, acc[10]); acc[11] = fmaf(w2.w, s, acc[11]);
+        }
+    }
+    if (!ok) return;
+    float mx = 0.f;
+#pragma unroll
+    for (int c = 0; c < 12; ++c) mx = fmaxf(mx, fabsf(acc[c]));
+    const float len = (mx < 1.1754943508222875e-38f) ? 1.0f : mx;
+    float* dst = out + size_t(td.pitch_off) * 12 + t;
+#pragma unroll
+    for (int c = 0; c < 12; ++c) dst[size_t(c) * td.ld] = acc[c] / len;
+}
+
+// workspace layout helpers ----------------------------------------------------------------
+static void pip_range(const ta_plan* plan, int& kmin, int& kmax) {
+    const double sr = plan->desc.sample_rate, fmax = std::min(4000.0, sr / 2.0), fmin = 150.0;
+    kmin = plan->n_bins;
+    kmax = 0;
+    for (int k = 0; k < plan->n_bins; ++k)
+        if (plan->h_freqs[k] >= fmin && plan->h_freqs[k] < fmax) {
+            kmin = std::min(kmin, k);
+            kmax = std::max(kmax, k + 1);
+        }
+    kmin = std::max(kmin, 1);
+    kmax = std::min(kmax, plan->n_bins - 1);
+}
+
+size_t chroma_scratch_bytes(const ta_plan* plan, const HostBatch& hb) {
+    int kmin, kmax;
+    pip_range(plan, kmin, kmax);
+    const size_t per_frame = size_t(std::max(1, (kmax - kmin + 1) / 2 + 1));
+    size_t peaks = 0;
+    for (auto& t : hb.tracks) peaks += per_frame * size_t(t.n_frames);
+    size_t bytes = 0;
+    auto add = [&](size_t b) { bytes = (bytes + b + 255) / 256 * 256; };
+    add(peaks * sizeof(float));
+    add(peaks);
+    add(sizeof(unsigned) * hb.n_tracks);
+    add(sizeof(size_t) * hb.n_tracks);
+    add(sizeof(float) * size_t(hb.n_tracks) * plan->n_bins * 12);
+    return bytes;
+}
+
+int run_chroma(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_tracks, const float* mag, const float* frame_max,
+               float* chroma, double* tuning, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+    TA_REQUIRE(plan->desc.n_chroma == 12, "only n_chroma = 12 is implemented");
+    TA_REQUIRE(hb.n_tracks <= 65535, "at most 65535 tracks per call");
+    TA_REQUIRE(scratch && scratch_bytes >= chroma_scratch_bytes(plan, hb), "chroma scratch too small");
+    int kmin, kmax;
+    pip_range(plan, kmin, kmax);
+    const size_t per_frame = size_t(std::max(1, (kmax - kmin + 1) / 2 + 1));
+    std::vector<size_t> off(hb.n_tracks);
+    size_t peaks = 0;
+    for (int i = 0; i < hb.n_tracks; ++i) {
+        off[i] = peaks;
+        peaks += per_frame * size_t(hb.tracks[i].n_frames);
+    }
+    unsigned char* base = reinterpret_cast<unsigned char*>(scratch);
+    size_t cur = 0;
+    auto take = [&](size_t b) {
+        unsigned char* r = base + cur;
+        cur = (cur + b + 255) / 256 * 256;
+        return r;
+    };
+    PeakList pl;
+    pl.mag = reinterpret_cast<float*>(take(peaks * sizeof(float)));
+    pl.bin = take(peaks);
+    pl.count = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * hb.n_tracks));
+    size_t* d_off = reinterpret_cast<size_t*>(take(sizeof(size_t) * hb.n_tracks));
+    float* fb = reinterpret_cast<float*>(take(sizeof(float) * size_t(hb.n_tracks) * plan->n_bins * 12));
+    pl.offset = d_off;
+    TA_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(size_t) * hb.n_tracks, cudaMemcpyHostToDevice, stream));
+    TA_CUDA(cudaMemsetAsync(pl.count, 0, sizeof(unsigned) * hb.n_tracks, stream));
+    const float bin_hz = float(double(plan->desc.sample_rate) / double(plan->desc.n_fft));
+    dim3 gf((hb.max_frames + 255) / 256, hb.n_tracks);
+    if (kmax > kmin) {
+        pip_peaks_kernel<<<gf, 256, 0, stream>>>(d_tracks, mag, frame_max, pl, plan->n_bins, kmin, kmax, bin_hz);
+        count_launch();
+        TA_CUDA(cudaGetLastError());
+    }
+    tuning_kernel<<<hb.n_tracks, 1024, 0, stream>>>(pl, tuning);
+    count_launch();
+    TA_CUDA(cudaGetLastError());
+    chroma_fb_kernel<<<dim3((plan->n_bins + 255) / 256, hb.n_tracks), 256, 0, stream>>>(tuning, fb, plan->n_bins, plan->desc.n_fft,
+                                                                                      double(plan->desc.sample_rate));
+    count_launch();
+    TA_CUDA(cudaGetLastError());
+    chroma_project_kernel<<<gf, 256, 0, stream>>>(d_tracks, mag, fb, chroma, plan->n_bins);
+    count_launch();
+    TA_CUDA(cudaGetLastError());
+    return TA_OK;
+}
+
+}  // namespace ta

@@ -60,6 +60,9 @@ struct ta_plan {
     int* d_mel_woff = nullptr;  // [n_mels]
     float* d_mel_w = nullptr;   // [nnz]
     int mel_nnz = 0;
+    float2* d_tg_tw1 = nullptr;   // tempogram transform (N = 1024) twiddles and window
+    float2* d_tg_tw2 = nullptr;
+    float* d_tg_window = nullptr;
     // host copies
     std::vector<float> h_window;
     std::vector<float> h_mel_dense;
@@ -92,7 +95,10 @@ struct Workspace {
     size_t gran_doubles;
     double* d_fft;             // autocorrelation scratch (complex double) [..]
     size_t fft_elems;
+    void* d_chroma;            // chroma_stft scratch (peak lists, filterbanks)
+    size_t chroma_bytes;
     unsigned char* end;
 };
+int stft_tile_frames(int n_fft);
 size_t carve_workspace(const ta_plan* plan, const HostBatch& hb, void* base, Workspace& ws);
 }  // namespace ta

@@ -29,7 +29,6 @@ int run_autocorrelate(const ta_plan*, const HostBatch&, const TrackDesc*, const 
                       double* scratch, size_t scratch_elems, cudaStream_t);
 size_t autocorr_scratch_elems(const HostBatch&);
 int run_time_domain(const ta_plan*, const HostBatch&, const Workspace&, const ta_frontend_out*, cudaStream_t);
-int stft_tile_frames(int n_fft);
 int time_chunk_samples(const ta_plan*, int64_t total_samples);
 
 // ---------------------------------------------------------------------------
@@ -171,6 +170,27 @@ static int plan_build(ta_plan* p) {
         p->mel_nnz = int(w.size());
     }
 
+    {   // tempogram: 1024-point transform twiddles and periodic Hann(win)
+        const int TN = 1024, TM = TN / 16, TQ = TN / 256;
+        std::vector<float2> t1(size_t(15) * TM), t2(size_t(16) * TQ);
+        for (int k1 = 1; k1 < 16; ++k1)
+            for (int r = 0; r < TM; ++r) {
+                const double a = -2.0 * PI * double((r * k1) % TN) / TN;
+                t1[size_t(k1 - 1) * TM + r] = make_float2(float(std::cos(a)), float(std::sin(a)));
+            }
+        for (int k2 = 0; k2 < 16; ++k2)
+            for (int n3 = 0; n3 < TQ; ++n3) {
+                const double a = -2.0 * PI * double(n3 * k2) / TM;
+                t2[size_t(k2) * TQ + n3] = make_float2(float(std::cos(a)), float(std::sin(a)));
+            }
+        const int win = std::max(2, d.tempogram_win);
+        std::vector<float> tw(win);
+        for (int n = 0; n < win; ++n) tw[n] = float(0.5 - 0.5 * std::cos(2.0 * PI * n / win));
+        if ((rc = upload(&p->d_tg_tw1, t1))) return rc;
+        if ((rc = upload(&p->d_tg_tw2, t2))) return rc;
+        if ((rc = upload(&p->d_tg_window, tw))) return rc;
+    }
+
     double coefs[12];
     biquad_kweight(d.sample_rate, p->shelf, p->highpass, coefs);
 
@@ -251,6 +271,10 @@ int build_host_batch(const ta_plan* plan, const ta_batch* b, HostBatch& hb) {
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 size_t td_granule_doubles(const ta_plan* plan, const HostBatch& hb);
+size_t chroma_scratch_bytes(const ta_plan* plan, const HostBatch& hb);
+int run_chroma(const ta_plan*, const HostBatch&, const TrackDesc*, const float* mag, const float* frame_max, float* chroma,
+               double* tuning, void* scratch, size_t scratch_bytes, cudaStream_t);
+int run_tempogram(const ta_plan*, const HostBatch&, const TrackDesc*, const float* env, float* out, cudaStream_t);
 
 size_t carve_workspace(const ta_plan* plan, const HostBatch& hb, void* base, Workspace& ws) {
     unsigned char* p = reinterpret_cast<unsigned char*>(base);
@@ -267,6 +291,8 @@ size_t carve_workspace(const ta_plan* plan, const HostBatch& hb, void* base, Wor
     ws.d_granules = reinterpret_cast<double*>(take(sizeof(double) * ws.gran_doubles));
     ws.fft_elems = autocorr_scratch_elems(hb);
     ws.d_fft = reinterpret_cast<double*>(take(sizeof(double) * ws.fft_elems));
+    ws.chroma_bytes = chroma_scratch_bytes(plan, hb);
+    ws.d_chroma = take(ws.chroma_bytes);
     ws.end = p ? p + off : nullptr;
     return off;
 }
@@ -318,6 +344,9 @@ void ta_plan_destroy(ta_plan* p) {
     cudaFree(p->d_mel_len);
     cudaFree(p->d_mel_woff);
     cudaFree(p->d_mel_w);
+    cudaFree(p->d_tg_tw1);
+    cudaFree(p->d_tg_tw2);
+    cudaFree(p->d_tg_window);
     delete p;
 }
 
@@ -420,6 +449,28 @@ int ta_time_domain(const ta_plan* plan, const ta_batch* batch, const ta_frontend
     return run_time_domain(plan, hb, ws, out, st);
 }
 
+int ta_chroma_stft(const ta_plan* plan, const ta_batch* batch, const float* magnitude, const float* frame_max, float* chroma,
+                   double* tuning, void* workspace, size_t workspace_bytes, void* stream) {
+    TA_REQUIRE(magnitude && frame_max && chroma && tuning, "magnitude/frame_max/chroma/tuning must not be NULL");
+    HostBatch hb;
+    Workspace ws;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = prepare(plan, batch, workspace, workspace_bytes, st, hb, ws);
+    if (rc != TA_OK) return rc;
+    return run_chroma(plan, hb, ws.d_tracks, magnitude, frame_max, chroma, tuning, ws.d_chroma, ws.chroma_bytes, st);
+}
+
+int ta_tempogram(const ta_plan* plan, const ta_batch* batch, const float* onset_env, float* tempogram, void* workspace,
+                 size_t workspace_bytes, void* stream) {
+    TA_REQUIRE(onset_env && tempogram, "onset_env/tempogram must not be NULL");
+    HostBatch hb;
+    Workspace ws;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = prepare(plan, batch, workspace, workspace_bytes, st, hb, ws);
+    if (rc != TA_OK) return rc;
+    return run_tempogram(plan, hb, ws.d_tracks, onset_env, tempogram, st);
+}
+
 uint64_t ta_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out, void* workspace,
@@ -432,10 +483,14 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
     if (rc != TA_OK) return rc;
     auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], st); };
     mark(0);
-    const bool need_flux = out->onset_env || out->flux_linear || out->autocorr;
+    const bool need_flux = out->onset_env || out->flux_linear || out->autocorr || out->tempogram;
     TA_REQUIRE(!need_flux || out->mel, "onset/autocorr outputs need the mel output buffer");
     TA_REQUIRE(!out->autocorr || out->onset_env, "autocorr output needs the onset_env output buffer");
-    const bool need_stft = out->magnitude || out->mel || out->ltas || out->centroid || out->rolloff_bin || out->band_energy;
+    TA_REQUIRE(!out->chroma || (out->magnitude && out->frame_max && out->tuning),
+               "chroma output needs the magnitude, frame_max and tuning buffers");
+    TA_REQUIRE(!out->tempogram || out->onset_env, "tempogram output needs the onset_env buffer");
+    const bool need_stft = out->magnitude || out->mel || out->ltas || out->centroid || out->rolloff_bin || out->band_energy ||
+                           out->frame_max;
     if (need_stft && (rc = run_stft_features(plan, hb, ws, out, st)) != TA_OK) return rc;
     mark(1);
     if (need_flux && (rc = run_onset_flux(plan, hb, ws.d_tracks, out->mel, ws.d_mel_max, out->onset_env,
@@ -444,6 +499,10 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
     mark(2);
     if (out->autocorr &&
         (rc = run_autocorrelate(plan, hb, ws.d_tracks, out->onset_env, out->autocorr, ws.d_fft, ws.fft_elems, st)) != TA_OK)
+        return rc;
+    if (out->tempogram && (rc = run_tempogram(plan, hb, ws.d_tracks, out->onset_env, out->tempogram, st)) != TA_OK) return rc;
+    if (out->chroma && (rc = run_chroma(plan, hb, ws.d_tracks, out->magnitude, out->frame_max, out->chroma, out->tuning,
+                                        ws.d_chroma, ws.chroma_bytes, st)) != TA_OK)
         return rc;
     mark(3);
     const bool need_td = out->moments || out->kw_blocks || out->lufs || out->rms_momentary || out->rms_short;

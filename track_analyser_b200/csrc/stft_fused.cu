@@ -43,6 +43,7 @@ struct StftParams {
     float* mel;
     double* centroid;
     int32_t* rolloff_bin;
+    float* frame_max;     // [P] max_f |X|
     double* ltas;         // [n_tracks][B]
     double* band_energy;  // [n_tracks][2][B]
     uint32_t* mel_max;    // [n_tracks]
@@ -299,23 +300,26 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
         // s1 = sum |X| and s2 = sum (k-kb)|X| (<= 65 terms each), combined across chunks in double:
         // centroid = df * sum_c (s2_c + kb_c*s1_c) / sum_c s1_c.  (librosa rounds |X|/sum to float32 before
         // the float64 dot product; that changes the result by ~2e-9 relative, far inside rtol 1e-4.)
-        if (p.centroid || p.rolloff_bin) {
+        if (p.centroid || p.rolloff_bin || p.frame_max) {
             constexpr int NCH = 16 * RPW;
             constexpr int CH = (B + NCH - 1) / NCH;
             float* part_1 = reinterpret_cast<float*>(ex_all);   // [NCH][TF]  (aliases the idle exchange buffers)
             float* part_2 = part_1 + NCH * TF;                  // [NCH][TF]
-            int* roll_s = reinterpret_cast<int*>(part_2 + NCH * TF);  // [TF]
+            float* part_3 = part_2 + NCH * TF;                  // [NCH][TF] chunk maxima
+            int* roll_s = reinterpret_cast<int*>(part_3 + NCH * TF);  // [TF]
             const int c = warp * RPW + sub;
             const int kb = c * CH, ke = min(kb + CH, B);
             const float* col = tile + f;
-            float s1 = 0.f, s2 = 0.f;
+            float s1 = 0.f, s2 = 0.f, s3 = 0.f;
             for (int k = kb; k < ke; ++k) {
                 const float a = col[k * TFP];
                 s1 += a;
                 s2 = fmaf(float(k - kb), a, s2);
+                s3 = fmaxf(s3, a);
             }
             part_1[c * TF + f] = s1;
             part_2[c * TF + f] = s2;
+            part_3[c * TF + f] = s3;
             if (tid < TF) roll_s[tid] = B;
             __syncthreads();
             float prefix = 0.f, total_f = 0.f;
@@ -345,6 +349,11 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
                 }
                 const double df = p.freqs[1];
                 p.centroid[col_out(td, t0, f)] = (den < 1.1754943508222875e-38) ? df * num : df * num / den;
+            }
+            if (c == 0 && fok && p.frame_max) {
+                float mx = 0.f;
+                for (int cc = 0; cc < NCH; ++cc) mx = fmaxf(mx, part_3[cc * TF + f]);
+                p.frame_max[col_out(td, t0, f)] = mx;
             }
             __syncthreads();
             if (c == 0 && fok && p.rolloff_bin) p.rolloff_bin[col_out(td, t0, f)] = roll_s[f];
@@ -395,6 +404,7 @@ int run_stft_features(const ta_plan* plan, const HostBatch& hb, const Workspace&
     p.mel = (plan->desc.n_mels > 0) ? out->mel : nullptr;
     p.centroid = out->centroid;
     p.rolloff_bin = out->rolloff_bin;
+    p.frame_max = out->frame_max;
     p.ltas = out->ltas;
     p.band_energy = out->band_energy;
     p.mel_max = p.mel ? ws.d_mel_max : nullptr;

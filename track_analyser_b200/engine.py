@@ -20,9 +20,12 @@ from . import _native as nat
 
 ALL_OUTPUTS = (
     "magnitude", "mel", "onset_env", "autocorr", "flux_linear", "ltas", "centroid", "rolloff_bin",
-    "band_energy", "moments", "kw_blocks", "lufs", "rms_momentary", "rms_short",
+    "band_energy", "moments", "kw_blocks", "lufs", "rms_momentary", "rms_short", "frame_max", "chroma", "tuning",
+    "tempogram",
 )
-DEFAULT_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o != "magnitude")
+# the bench / default frontend: everything the per-track analysis consumes except the plot-only tempogram
+CORE_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o != "tempogram")
+DEFAULT_OUTPUTS = tuple(o for o in CORE_OUTPUTS if o != "magnitude")
 
 
 def frame_count(n_samples: int, hop: int) -> int:
@@ -55,6 +58,7 @@ class Plan:
                  device: int | None = None, fmin: float = 0.0, fmax: float | None = None,
                  roll_percent: float = 0.85, meter_block: float = 0.4, n_chroma: int = 12,
                  tempogram_win: int = 384):
+        self.tempogram_win = int(tempogram_win)
         if not torch.cuda.is_available():
             raise RuntimeError("track_analyser_b200 needs a CUDA device (B200); there is no CPU fallback")
         self.lib = nat.load()
@@ -160,8 +164,14 @@ class FrontendBuffers:
             raise ValueError(f"unknown outputs {sorted(unknown)}")
         if outputs & {"onset_env", "autocorr", "flux_linear"}:
             outputs.add("mel")
-        if "autocorr" in outputs:
+        if outputs & {"autocorr", "tempogram"}:
             outputs.add("onset_env")
+        if "chroma" in outputs:
+            outputs |= {"magnitude", "frame_max", "tuning"}
+        if "tuning" in outputs:
+            outputs |= {"magnitude", "frame_max", "chroma"}
+        if outputs & {"onset_env", "autocorr", "flux_linear", "tempogram"}:
+            outputs.add("mel")
         max_ns = int(batch.n_samples.max()) if nt else 0
         self.kw_pitch = max(1, plan.kw_block_count(max_ns))
         self.rms_pitch = 1 + max_ns // plan.rms_frames(plan.meter_block)[1]
@@ -173,6 +183,8 @@ class FrontendBuffers:
             "band_energy": ((nt, 2, B), torch.float64), "moments": ((nt, 8), torch.float64),
             "kw_blocks": ((nt, self.kw_pitch), torch.float64), "lufs": ((nt,), torch.float64),
             "rms_momentary": ((nt, self.rms_pitch), torch.float64), "rms_short": ((nt, self.rms_pitch), torch.float64),
+            "frame_max": ((P,), torch.float32), "chroma": ((12 * P,), torch.float32), "tuning": ((nt,), torch.float64),
+            "tempogram": ((plan.tempogram_win * P,), torch.float32),
         }
         self.t = {k: torch.empty(shapes[k][0], dtype=shapes[k][1], device=dev) for k in ALL_OUTPUTS if k in outputs}
         self.c_out = nat.FrontendOut()
@@ -233,7 +245,14 @@ def download(batch: DeviceBatch, bufs: FrontendBuffers) -> list[TrackResult]:
                 r.data[k] = h[B * po: B * (po + ld)].reshape(B, ld)[:, :T]
             elif k == "mel":
                 r.data[k] = h[M * po: M * (po + ld)].reshape(M, ld)[:, :T]
-            elif k in ("onset_env", "autocorr", "flux_linear", "centroid", "rolloff_bin"):
+            elif k == "chroma":
+                r.data[k] = h[12 * po: 12 * (po + ld)].reshape(12, ld)[:, :T]
+            elif k == "tempogram":
+                W = plan.tempogram_win
+                r.data[k] = h[W * po: W * (po + ld)].reshape(W, ld)[:, :T]
+            elif k == "tuning":
+                r.data[k] = float(h[i])
+            elif k in ("onset_env", "autocorr", "flux_linear", "centroid", "rolloff_bin", "frame_max"):
                 r.data[k] = h[po: po + T]
             elif k == "kw_blocks":
                 r.data[k] = h[i, : plan.kw_block_count(ns)]
