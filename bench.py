@@ -231,7 +231,7 @@ def ours(args, rank, world, local_rank):
         engine.run_device(plan, batch, bufs)
     barrier()
     launches0 = engine.launch_count()
-    stage = np.zeros(4)
+    stage = np.zeros(len(engine.STAGE_NAMES))
     with ClockSampler(local_rank) as clk:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -291,8 +291,7 @@ def ours(args, rank, world, local_rank):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_kernel_max, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world),
-            "stage_ms": {"stft_mel_features": stage[0], "onset_flux": stage[1], "autocorrelation": stage[2],
-                         "time_domain_loudness": stage[3]},
+            "stage_ms": {k: float(v) for k, v in zip(engine.STAGE_NAMES, stage)},
             "roofline": {"bound": "hbm", "kernel": "stft_fused_kernel<2048,32,stereo>", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",

@@ -133,10 +133,12 @@ TA_API int ta_frontend_run(const ta_plan* plan, const ta_batch* batch, const ta_
 /* Same schedule as ta_frontend_run, but brackets each stage with CUDA events on
  * `stream`, synchronises, and returns the device time of each stage in
  * milliseconds: stage_ms[0] STFT+mel+features (K1/K2/K7), [1] onset flux (K3),
- * [2] autocorrelation (K4), [3] time-domain pass + gating (K5/K6).  For bench.py's
- * roofline figure; not for production use (it blocks the host). */
+ * [2] autocorrelation (K4), [3] tempogram (K4b), [4] chroma_stft (K2b),
+ * [5] time-domain pass + gating (K5/K6).  For bench.py's roofline figure; not for
+ * production use (it blocks the host). */
+#define TA_N_STAGES 6
 TA_API int ta_frontend_run_profiled(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out,
-                                    void* workspace, size_t workspace_bytes, void* stream, float stage_ms[4]);
+                                    void* workspace, size_t workspace_bytes, void* stream, float stage_ms[TA_N_STAGES]);
 
 /* Number of kernels this library has launched in the calling process so far. */
 TA_API uint64_t ta_launch_count(void);

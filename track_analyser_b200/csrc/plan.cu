@@ -500,14 +500,16 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
     if (out->autocorr &&
         (rc = run_autocorrelate(plan, hb, ws.d_tracks, out->onset_env, out->autocorr, ws.d_fft, ws.fft_elems, st)) != TA_OK)
         return rc;
+    mark(3);
     if (out->tempogram && (rc = run_tempogram(plan, hb, ws.d_tracks, out->onset_env, out->tempogram, st)) != TA_OK) return rc;
+    mark(4);
     if (out->chroma && (rc = run_chroma(plan, hb, ws.d_tracks, out->magnitude, out->frame_max, out->chroma, out->tuning,
                                         ws.d_chroma, ws.chroma_bytes, st)) != TA_OK)
         return rc;
-    mark(3);
+    mark(5);
     const bool need_td = out->moments || out->kw_blocks || out->lufs || out->rms_momentary || out->rms_short;
     if (need_td && (rc = run_time_domain(plan, hb, ws, out, st)) != TA_OK) return rc;
-    mark(4);
+    mark(6);
     return TA_OK;
 }
 
@@ -517,15 +519,15 @@ int ta_frontend_run(const ta_plan* plan, const ta_batch* batch, const ta_fronten
 }
 
 int ta_frontend_run_profiled(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out, void* workspace,
-                             size_t workspace_bytes, void* stream, float stage_ms[4]) {
+                             size_t workspace_bytes, void* stream, float stage_ms[TA_N_STAGES]) {
     TA_REQUIRE(stage_ms, "stage_ms must not be NULL");
-    cudaEvent_t ev[5];
+    cudaEvent_t ev[TA_N_STAGES + 1];
     for (auto& e : ev) TA_CUDA(cudaEventCreate(&e));
     int rc = frontend_impl(plan, batch, out, workspace, workspace_bytes, stream, ev);
     if (rc == TA_OK) {
-        cudaError_t e = cudaEventSynchronize(ev[4]);
+        cudaError_t e = cudaEventSynchronize(ev[TA_N_STAGES]);
         if (e != cudaSuccess) rc = cuda_fail(e, "cudaEventSynchronize", __FILE__, __LINE__);
-        for (int i = 0; i < 4 && rc == TA_OK; ++i) cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]);
+        for (int i = 0; i < TA_N_STAGES && rc == TA_OK; ++i) cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]);
     }
     for (auto& e : ev) cudaEventDestroy(e);
     return rc;

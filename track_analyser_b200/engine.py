@@ -28,6 +28,9 @@ CORE_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o != "tempogram")
 DEFAULT_OUTPUTS = tuple(o for o in CORE_OUTPUTS if o != "magnitude")
 
 
+STAGE_NAMES = ("stft_mel_features", "onset_flux", "autocorrelation", "tempogram", "chroma_stft", "time_domain_loudness")
+
+
 def frame_count(n_samples: int, hop: int) -> int:
     return 1 + n_samples // hop
 
@@ -217,10 +220,10 @@ def run_device(plan: Plan, batch: DeviceBatch, bufs: FrontendBuffers, stage: str
 
 
 def run_device_profiled(plan: Plan, batch: DeviceBatch, bufs: FrontendBuffers) -> list[float]:
-    """Fused frontend with per-stage device times (ms): [stft+mel+features, onset, autocorr, time-domain]."""
+    """Fused frontend with per-stage device times (ms): see STAGE_NAMES."""
     ws = workspace(plan, batch)
     stream = C.c_void_p(torch.cuda.current_stream(batch.pcm.device).cuda_stream)
-    ms = (C.c_float * 4)()
+    ms = (C.c_float * len(STAGE_NAMES))()
     nat.check(plan.lib.ta_frontend_run_profiled(plan._h, C.byref(batch.c_batch), C.byref(bufs.c_out),
                                                 C.c_void_p(ws.data_ptr()), ws.numel(), stream, ms))
     return list(ms)
