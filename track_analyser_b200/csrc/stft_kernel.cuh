@@ -1,0 +1,456 @@
+// K1 + K2(mel) + K7: fused frame + Hann + FFT + |X| kernel with in-CTA epilogue.
+//
+// Replaces, per track, every mono/mid and side STFT of the reference
+// (features.py:79,97,116; stereo.py:95-96; structure.py:48,53; tempo.py:19 via
+// melspectrogram; harmony.py:254) with ONE complex FFT per frame (stereo: z = mid + i*side) or
+// per two frames (mono: z = frame_a + i*frame_b), split afterwards by Hermitian symmetry -- and
+// every thread carries TWO such transforms in packed f32x2 registers (fft2_core.cuh), so one
+// "slot" of work is 2 stereo frames or 4 mono frames.
+//
+// A persistent CTA (one per SM, 512 threads = NG groups of N/16 threads) walks a contiguous range
+// of (track, tile) work items; a tile is TF consecutive frames.
+// Per tile:   FFT phase   each group transforms slots g, g+NG, ... and writes |X_mid| pairs into a
+//                         shared [bin][frame] tile (pitch TF+2 floats; (TF+2)/2 odd keeps the 64-bit
+//                         column-pair stores and the row reads conflict free); per-bin sums of
+//                         |side|^2 stay in registers across the tiles of a track.
+//             epilogue    (a) magnitude tile -> global, row segments of TF contiguous floats;
+//                             per-bin time sums (LTAS, |mid|^2), one thread per bin
+//                         (b) sparse Slaney mel projection of tile^2 -> global (two frames per thread)
+//                         (c) per-frame centroid / roll-off / max: one warp per frame pair, one bin chunk
+//                             per lane, warp scans instead of shared-memory partials
+// Algorithmic HBM bytes per tile: read C*TF*hop*4 (PCM), write (B+M)*TF*4 + 16*TF.
+#pragma once
+#include <algorithm>
+
+#include "common.cuh"
+#include "fft2_core.cuh"
+#include "stft_params.cuh"
+
+namespace ta {
+
+
+// |X| = sqrt(re^2+im^2) through MUFU.SQRT (max rel. error 2^-22): two orders of magnitude below the
+// fp32 FFT's own rounding noise and 1e3 below the parity tolerance, at a quarter of __fsqrt_rn's cost.
+__device__ __forceinline__ float fast_sqrt(float x) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ void group_barrier(int g, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
+}
+
+template <int N, int TF, bool STEREO>
+struct StftCfg {
+    using C = FftCfg<N>;
+    static constexpr int THREADS = 512;
+    static constexpr int NG = THREADS / C::M;     // transform groups per CTA
+    static constexpr int B = N / 2 + 1;
+    static constexpr int FPS = STEREO ? 2 : 4;    // frames per slot (two packed transforms)
+    static constexpr int SLOTS = TF / FPS;
+    static constexpr int TFP = TF + 2;            // tile row pitch (floats)
+    static constexpr int HP = TF / 2;             // frame pairs per tile
+    static constexpr int NACC = (B + THREADS - 1) / THREADS;
+    static constexpr int CH = (B + 31) / 32;      // bins per lane in the per-frame feature pass
+    static_assert(SLOTS % NG == 0, "tile must hold a whole number of rounds");
+    static_assert((TFP / 2) % 2 == 1, "tile pitch / 2 must be odd");
+    static constexpr size_t tile_bytes = ((size_t(B) * TFP * 4 + 15) / 16) * 16;
+    static constexpr size_t ex_bytes = size_t(NG) * p2::Ex<N>::SLOTS * 16;
+    static constexpr bool TW1_SMEM = (N != 4096);  // 4096: tile + exchange leave no room, read tw1 through L2
+    static constexpr size_t tw1_bytes = TW1_SMEM ? size_t(15) * C::M * 8 : 0;
+    static constexpr size_t tw2_bytes = size_t(16) * C::Q * 8;
+    static constexpr size_t fixed = tile_bytes + ex_bytes + tw1_bytes + tw2_bytes;
+    __host__ __device__ static size_t mel_tab_bytes(int n_mels) { return ((size_t(3) * n_mels * 4 + 15) / 16) * 16; }
+    __host__ __device__ static size_t mel_w_bytes(int mel_nnz) { return ((size_t(mel_nnz) * 4 + 15) / 16) * 16; }
+};
+
+static constexpr size_t SMEM_LIMIT = 232448;  // 227 KB opt-in maximum per CTA on sm_100
+
+__device__ __forceinline__ size_t col_out(const TrackDesc& td, int t0, int f) { return size_t(td.pitch_off) + t0 + f; }
+
+// mel band m, frame pair fp: sum_j w[j] * tile[ks+j][2fp..2fp+1]^2
+template <int TFP>
+__device__ __forceinline__ float2 mel_taps(const float* __restrict__ col, const float* __restrict__ wt, int len) {
+    using namespace p2;
+    float2 a0 = make_float2(0.f, 0.f), a1 = a0;
+    int j = 0;
+    for (; j + 2 <= len; j += 2) {
+        const float2 x0 = *reinterpret_cast<const float2*>(col + (j + 0) * TFP);
+        const float2 x1 = *reinterpret_cast<const float2*>(col + (j + 1) * TFP);
+        a0 = pfmas(pmul(x0, x0), wt[j + 0], a0);
+        a1 = pfmas(pmul(x1, x1), wt[j + 1], a1);
+    }
+    if (j < len) {
+        const float2 x0 = *reinterpret_cast<const float2*>(col + j * TFP);
+        a0 = pfmas(pmul(x0, x0), wt[j], a0);
+    }
+    return padd(a0, a1);
+}
+
+// SH > 0: hop == SH * (N/16), so frame q of a slot reads the samples of frame 0 shifted by q*SH rows of the
+// (16, N/16) sample matrix and each thread loads 16 + (frames-1)*SH values per channel instead of 16 per frame.
+template <int N, int TF, bool STEREO, int SH>
+__global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) {
+    using namespace p2;
+    using C = FftCfg<N>;
+    using S = StftCfg<N, TF, STEREO>;
+    using E = Ex<N>;
+    constexpr int M = C::M, NG = S::NG, B = S::B, TFP = S::TFP, HP = S::HP, NACC = S::NACC, CH = S::CH;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* tile = reinterpret_cast<float*>(smem_raw);
+    float4* ex_all = reinterpret_cast<float4*>(smem_raw + S::tile_bytes);
+    float2* tw1s = reinterpret_cast<float2*>(smem_raw + S::tile_bytes + S::ex_bytes);
+    float2* tw2s = reinterpret_cast<float2*>(smem_raw + S::tile_bytes + S::ex_bytes + S::tw1_bytes);
+    int* mel_tab = reinterpret_cast<int*>(smem_raw + S::fixed);  // [3][n_mels]: start, len, woff
+    float* mel_ws = reinterpret_cast<float*>(smem_raw + S::fixed + S::mel_tab_bytes(p.n_mels));
+
+    const int tid = threadIdx.x;
+    const int g = tid / M, r = tid % M;
+    const int warp = tid >> 5, lane = tid & 31;
+    float4* ex = ex_all + size_t(g) * E::SLOTS;
+
+    if (S::TW1_SMEM)
+        for (int i = tid; i < 15 * M; i += S::THREADS) tw1s[i] = p.tw1[i];
+    const float2* tw1 = S::TW1_SMEM ? tw1s : p.tw1;
+    for (int i = tid; i < 16 * C::Q; i += S::THREADS) tw2s[i] = p.tw2[i];
+    if (p.mel) {
+        for (int i = tid; i < p.n_mels; i += S::THREADS) {
+            mel_tab[i] = p.mel_start[i];
+            mel_tab[p.n_mels + i] = p.mel_len[i];
+            mel_tab[2 * p.n_mels + i] = p.mel_woff[i];
+        }
+        if (p.mel_in_smem)
+            for (int i = tid; i < p.mel_nnz; i += S::THREADS) mel_ws[i] = p.mel_w[i];
+    }
+    // window, pre-scaled: 1/2 for the Hermitian split, another 1/2 for (L+-R)/2
+    float wreg[16];
+#pragma unroll
+    for (int n1 = 0; n1 < 16; ++n1) wreg[n1] = p.window[n1 * M + r] * (STEREO ? 0.25f : 0.5f);
+    __syncthreads();
+
+    const int w0 = int((long long)blockIdx.x * p.total_tiles / gridDim.x);
+    const int w1 = int((long long)(blockIdx.x + 1) * p.total_tiles / gridDim.x);
+    if (w0 >= w1) return;
+
+    int trk = 0;
+    {
+        int lo = 0, hi = p.n_tracks - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (p.tracks[mid].tile_begin <= w0) lo = mid; else hi = mid - 1;
+        }
+        trk = lo;
+    }
+
+    float acc_s[9];            // sum_t |side[k]|^2 for the 8 kept bins (+ bin N/2 on r == 0)
+    float acc_l[NACC], acc_m[NACC];  // sum_t |mid[k]|, |mid[k]|^2 for bins tid + 512*j
+#pragma unroll
+    for (int i = 0; i < 9; ++i) acc_s[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NACC; ++j) acc_l[j] = acc_m[j] = 0.f;
+
+    auto flush = [&](int t) {
+        if (STEREO && p.band_energy) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                atomicAdd(&p.band_energy[(size_t(t) * 2 + 1) * B + kept_bin<N>(r, i)], double(acc_s[i]));
+            if (r == 0) atomicAdd(&p.band_energy[(size_t(t) * 2 + 1) * B + N / 2], double(acc_s[8]));
+        }
+#pragma unroll
+        for (int i = 0; i < 9; ++i) acc_s[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < NACC; ++j) {
+            const int k = tid + S::THREADS * j;
+            if (k < B) {
+                if (p.ltas) atomicAdd(&p.ltas[size_t(t) * B + k], double(acc_l[j]));
+                if (p.band_energy) atomicAdd(&p.band_energy[(size_t(t) * 2 + 0) * B + k], double(acc_m[j]));
+            }
+            acc_l[j] = acc_m[j] = 0.f;
+        }
+    };
+
+    for (int w = w0; w < w1; ++w) {
+        while (trk + 1 < p.n_tracks && w >= p.tracks[trk + 1].tile_begin) {
+            flush(trk);
+            ++trk;
+        }
+        const TrackDesc td = p.tracks[trk];
+        const int t0 = (w - td.tile_begin) * TF;
+        const int nf = min(TF, td.n_frames - t0);
+
+        // ------------------------------ FFT phase ------------------------------
+        // Every slot of the tile is transformed, frames past the end of the track as zeros, so the
+        // whole tile is defined for the epilogue.
+        for (int s = g; s < S::SLOTS; s += NG) {
+            const int f = s * S::FPS;                // first frame of the slot inside the tile
+            const int t = t0 + f;                    // absolute frame
+            const long long base = (long long)t * p.hop - N / 2;
+            C2 v[16];
+            constexpr int NFR = S::FPS;  // frames per slot
+            const bool interior = t + NFR - 1 < td.n_frames && base >= 0 && base + (long long)(NFR - 1) * p.hop + N <= td.n_samples;
+            if (SH > 0 && interior) {
+                // L2 prefetch of the rows this group's next slot adds (NG slots further on in the same track)
+                {
+                    const long long nb = base + (long long)NG * NFR * p.hop + (long long)r * 32;
+                    if (r * 32 < (16 + (NFR - 1) * SH) * M && nb + 32 <= td.n_samples) {
+                        prefetch_l2(td.ch0 + nb);
+                        if (STEREO) prefetch_l2(td.ch1 + nb);
+                    }
+                }
+                if (STEREO) {
+                    const float* __restrict__ La = td.ch0 + base + r;
+                    const float* __restrict__ Ra = td.ch1 + base + r;
+                    float m[16 + SH], sd[16 + SH];
+#pragma unroll
+                    for (int j = 0; j < 16 + SH; ++j) {
+                        const float l = __ldg(La + j * M), rr = __ldg(Ra + j * M);
+                        m[j] = l + rr;
+                        sd[j] = l - rr;
+                    }
+#pragma unroll
+                    for (int n1 = 0; n1 < 16; ++n1) {
+                        v[n1].re = make_float2(m[n1] * wreg[n1], m[n1 + SH] * wreg[n1]);
+                        v[n1].im = make_float2(sd[n1] * wreg[n1], sd[n1 + SH] * wreg[n1]);
+                    }
+                } else {
+                    const float* __restrict__ Xa = td.ch0 + base + r;
+                    float x[16 + 3 * SH];
+#pragma unroll
+                    for (int j = 0; j < 16 + 3 * SH; ++j) x[j] = __ldg(Xa + j * M);
+#pragma unroll
+                    for (int n1 = 0; n1 < 16; ++n1) {
+                        v[n1].re = make_float2(x[n1] * wreg[n1], x[n1 + SH] * wreg[n1]);
+                        v[n1].im = make_float2(x[n1 + 2 * SH] * wreg[n1], x[n1 + 3 * SH] * wreg[n1]);
+                    }
+                }
+            } else if (STEREO) {
+                const float* __restrict__ L = td.ch0;
+                const float* __restrict__ R = td.ch1;
+                const bool va = t < td.n_frames, vb = t + 1 < td.n_frames;
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) {
+                    const long long na = base + n1 * M + r, nb = na + p.hop;
+                    const bool oka = va && na >= 0 && na < td.n_samples, okb = vb && nb >= 0 && nb < td.n_samples;
+                    const float2 l = make_float2(oka ? __ldg(L + na) : 0.f, okb ? __ldg(L + nb) : 0.f);
+                    const float2 rr = make_float2(oka ? __ldg(R + na) : 0.f, okb ? __ldg(R + nb) : 0.f);
+                    v[n1].re = pmuls(padd(l, rr), wreg[n1]);
+                    v[n1].im = pmuls(psub(l, rr), wreg[n1]);
+                }
+            } else {
+                // transform A = frame t + i*frame t+2, transform B = frame t+1 + i*frame t+3: the two real
+                // spectra of a packed pair are then adjacent frames (t, t+1) and (t+2, t+3).
+                const float* __restrict__ X = td.ch0;
+#pragma unroll
+                for (int n1 = 0; n1 < 16; ++n1) {
+                    float x[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const long long n = base + (long long)q * p.hop + n1 * M + r;
+                        x[q] = (t + q < td.n_frames && n >= 0 && n < td.n_samples) ? __ldg(X + n) : 0.f;
+                    }
+                    v[n1].re = pmuls(make_float2(x[0], x[1]), wreg[n1]);
+                    v[n1].im = pmuls(make_float2(x[2], x[3]), wreg[n1]);
+                }
+            }
+            pass1<N>(v, r, tw1, ex);
+            group_barrier(g, M);
+            pass2<N>(v, r, tw2s, ex);
+            group_barrier(g, M);
+            pass3<N>(v, r, ex);
+            group_barrier(g, M);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int k = kept_bin<N>(r, i);
+                const C2 zk = v[kept_reg<N>(i)];
+                C2 zn = unpack(ex[E::slot_of((N - k) & (N - 1))]);
+                if (i == 0 && r == 0) zn = zk;  // bin 0 mirrors itself
+                C2 xa, xb;
+                split_pair(zk, zn, xa, xb);
+                const float2 pa = pfma(xa.re, xa.re, pmul(xa.im, xa.im));
+                const float2 pb = pfma(xb.re, xb.re, pmul(xb.im, xb.im));
+                *reinterpret_cast<float2*>(tile + k * TFP + f) = make_float2(fast_sqrt(pa.x), fast_sqrt(pa.y));
+                if (STEREO) acc_s[i] += pb.x + pb.y;
+                else *reinterpret_cast<float2*>(tile + k * TFP + f + 2) = make_float2(fast_sqrt(pb.x), fast_sqrt(pb.y));
+            }
+            if (r == 0) {  // bin N/2 (thread 0, butterfly 0, k3 = Q/2) mirrors itself
+                const C2 z = v[C::Q / 2];
+                C2 xa, xb;
+                split_pair(z, z, xa, xb);
+                const float2 pa = pfma(xa.re, xa.re, pmul(xa.im, xa.im));
+                const float2 pb = pfma(xb.re, xb.re, pmul(xb.im, xb.im));
+                *reinterpret_cast<float2*>(tile + (N / 2) * TFP + f) = make_float2(fast_sqrt(pa.x), fast_sqrt(pa.y));
+                if (STEREO) acc_s[8] += pb.x + pb.y;
+                else *reinterpret_cast<float2*>(tile + (N / 2) * TFP + f + 2) = make_float2(fast_sqrt(pb.x), fast_sqrt(pb.y));
+            }
+            group_barrier(g, M);  // mirror reads done before the next slot's pass 1 overwrites the slots
+        }
+        __syncthreads();
+
+        // ------------------------------ epilogue ------------------------------
+        {   // (a) magnitude rows -> global (64-bit stores, TF contiguous floats per row).  A half-warp reads RPH rows
+            // that are D rows apart so that its 16 64-bit words fall into 16 distinct bank pairs.
+            constexpr int RPH = 16 / HP, D = (TF == 16) ? 8 : (TF == 8) ? 4 : 1, RB = D * RPH;
+            const int hw = tid >> 4, l16 = tid & 15, fp = l16 % HP, ri = l16 / HP;
+            const bool ok0 = 2 * fp < nf, ok1 = 2 * fp + 1 < nf;
+            if (p.mag) {
+                float* dst = p.mag + size_t(td.pitch_off) * B + t0 + 2 * fp;
+                for (int q = hw; (q / D) * RB < B; q += S::THREADS / 16) {
+                    const int k = (q / D) * RB + (q % D) + ri * D;
+                    if (k < B && ok0) {
+                        const float2 a = *reinterpret_cast<const float2*>(tile + k * TFP + 2 * fp);
+                        if (ok1) *reinterpret_cast<float2*>(dst + size_t(k) * td.ld) = a;
+                        else dst[size_t(k) * td.ld] = a.x;
+                    }
+                }
+            }
+            // ... and per-bin time sums, one thread per bin (frames past the track end are exact zeros)
+            if (p.ltas || p.band_energy) {
+#pragma unroll
+                for (int j = 0; j < NACC; ++j) {
+                    const int k = tid + S::THREADS * j;
+                    if (k < B) {
+                        const float* row = tile + k * TFP;
+                        float2 s = make_float2(0.f, 0.f), q = s;
+#pragma unroll
+                        for (int h = 0; h < HP; ++h) {
+                            const float2 a = *reinterpret_cast<const float2*>(row + 2 * h);
+                            s = padd(s, a);
+                            q = pfma(a, a, q);
+                        }
+                        acc_l[j] += s.x + s.y;
+                        acc_m[j] += q.x + q.y;
+                    }
+                }
+            }
+        }
+        // (b) mel projection of tile^2 (power = magnitude**2 as librosa computes it), two frames per thread
+        if (p.mel) {
+            float vmax = 0.f;
+            for (int it = tid; it < p.n_mels * HP; it += S::THREADS) {
+                const int fp = it % HP, m = it / HP;
+                const int ks = mel_tab[m], len = mel_tab[p.n_mels + m], wo = mel_tab[2 * p.n_mels + m];
+                const float* col = tile + ks * TFP + 2 * fp;
+                const float2 acc = p.mel_in_smem ? mel_taps<TFP>(col, mel_ws + wo, len) : mel_taps<TFP>(col, p.mel_w + wo, len);
+                float* dst = p.mel + size_t(td.pitch_off) * p.n_mels + size_t(m) * td.ld + t0 + 2 * fp;
+                if (2 * fp + 1 < nf) {
+                    *reinterpret_cast<float2*>(dst) = acc;
+                    vmax = fmaxf(vmax, fmaxf(acc.x, acc.y));
+                } else if (2 * fp < nf) {
+                    dst[0] = acc.x;
+                    vmax = fmaxf(vmax, acc.x);
+                }
+            }
+            if (p.mel_max) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+                if (lane == 0) atomicMax(&p.mel_max[trk], __float_as_uint(vmax));
+            }
+        }
+        // (c) per-frame centroid / roll-off / max: warp per frame, lane c owns bins [c*CH, c*CH+CH).
+        // fp32 chunk sums s1 = sum |X|, s2 = sum (k-kb)|X|; centroid = df * sum_c (s2_c + kb_c*s1_c) / sum_c s1_c
+        // combined in double.  (librosa rounds |X|/sum to float32 before the float64 dot product; that changes
+        // the result by ~2e-9 relative.)  Roll-off: first bin whose running float32 sum reaches 0.85*total:
+        // warp scan over the chunk sums finds the chunk, a second scan inside that chunk finds the bin.
+        if (p.centroid || p.rolloff_bin || p.frame_max) {
+            for (int fp = warp; 2 * fp < nf; fp += S::THREADS / 32) {   // warp per frame PAIR: one 64-bit read serves both
+                const float* col = tile + 2 * fp;
+                const int kb = lane * CH, ke = min(kb + CH, B);
+                float2 q1 = make_float2(0.f, 0.f), q2 = q1, q3 = q1;
+                float kf = 0.f;
+                for (int k = kb; k < ke; ++k) {
+                    const float2 a = *reinterpret_cast<const float2*>(col + k * TFP);
+                    q1 = padd(q1, a);
+                    q2 = pfmas(a, kf, q2);
+                    q3.x = fmaxf(q3.x, a.x);
+                    q3.y = fmaxf(q3.y, a.y);
+                    kf += 1.0f;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int f = 2 * fp + h;
+                    if (f >= nf) break;  // warp-uniform
+                    const float s1 = h ? q1.y : q1.x, s2 = h ? q2.y : q2.x;
+                    float s3 = h ? q3.y : q3.x;
+                    float incl = s1;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const float u = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += u;
+                    }
+                    const float total = __shfl_sync(0xffffffffu, incl, 31);
+                    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+                    if (lane == 0) excl = 0.f;
+                    const float thr = p.roll_percent * total;
+                    if (p.rolloff_bin) {
+                        const unsigned hit = __ballot_sync(0xffffffffu, !(incl < thr));
+                        const int cstar = hit ? __ffs(hit) - 1 : 31;
+                        float carry = __shfl_sync(0xffffffffu, excl, cstar);
+                        const int kb2 = cstar * CH, ke2 = min(kb2 + CH, B);
+                        int first = ke2 - 1;
+                        for (int i0 = kb2; i0 < ke2; i0 += 32) {
+                            const int k = i0 + lane;
+                            float run = (k < ke2) ? col[k * TFP + h] : 0.f;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const float u = __shfl_up_sync(0xffffffffu, run, o);
+                                if (lane >= o) run += u;
+                            }
+                            run += carry;
+                            const unsigned h2 = __ballot_sync(0xffffffffu, k < ke2 && !(run < thr));
+                            if (h2) {
+                                first = i0 + __ffs(h2) - 1;
+                                break;
+                            }
+                            carry = __shfl_sync(0xffffffffu, run, 31);
+                        }
+                        if (lane == 0) p.rolloff_bin[col_out(td, t0, f)] = first;
+                    }
+                    if (p.centroid) {
+                        double den = double(s1), num = double(s2) + double(kb) * double(s1);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            den += __shfl_xor_sync(0xffffffffu, den, o);
+                            num += __shfl_xor_sync(0xffffffffu, num, o);
+                        }
+                        if (lane == 0) {
+                            const double df = p.freqs[1];
+                            p.centroid[col_out(td, t0, f)] = (den < 1.1754943508222875e-38) ? df * num : df * num / den;
+                        }
+                    }
+                    if (p.frame_max) {
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) s3 = fmaxf(s3, __shfl_xor_sync(0xffffffffu, s3, o));
+                        if (lane == 0) p.frame_max[col_out(td, t0, f)] = s3;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    flush(trk);
+}
+
+template <int N, int TF, bool STEREO, int SH>
+static int launch_stft(const ta_plan* plan, StftParams p, cudaStream_t stream) {
+    using S = StftCfg<N, TF, STEREO>;
+    auto kern = stft_fused_kernel<N, TF, STEREO, SH>;
+    size_t smem = S::fixed + S::mel_tab_bytes(p.n_mels);
+    p.mel_in_smem = (smem + S::mel_w_bytes(p.mel_nnz) <= SMEM_LIMIT) ? 1 : 0;
+    if (p.mel_in_smem) smem += S::mel_w_bytes(p.mel_nnz);
+    if (smem > SMEM_LIMIT) {
+        set_error("mel band table does not fit in shared memory next to the STFT tile");
+        return TA_ERR_UNSUPPORTED;
+    }
+    TA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::max(1, std::min(plan->sm_count, p.total_tiles));
+    kern<<<grid, 512, smem, stream>>>(p);
+    count_launch();
+    TA_CUDA(cudaGetLastError());
+    return TA_OK;
+}
+
+}  // namespace ta

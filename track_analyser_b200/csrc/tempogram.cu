@@ -74,11 +74,11 @@ __global__ void __launch_bounds__(512, 1) tempogram_kernel(const TgParams p) {
         int lo = 0, hi = p.n_tracks - 1;
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
-            if (p.tracks[mid].tile_begin <= w) lo = mid; else hi = mid - 1;
+            if (p.tracks[mid].pitch_off <= (long long)w * TG_TF) lo = mid; else hi = mid - 1;
         }
         const TrackDesc td = p.tracks[lo];
         const int T = td.n_frames;
-        const int t0 = (w - td.tile_begin) * TG_TF;
+        const int t0 = int((long long)w * TG_TF - td.pitch_off);  // frame pitches are multiples of 32: tiles = pitch / 32
         const int nf = min(TG_TF, T - t0);
         const float* __restrict__ x = p.env + td.pitch_off;
         const int slots = (nf + 1) / 2;
@@ -170,11 +170,10 @@ int run_tempogram(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_t
     using C = FftCfg<TG_N>;
     const int win = plan->desc.tempogram_win;
     TA_REQUIRE(win >= 2 && win <= 512 && win % 2 == 0, "tempogram window must be even and <= 512 frames");
-    TA_REQUIRE(stft_tile_frames(plan->desc.n_fft) == TG_TF, "tempogram needs the 32-frame tiling (n_fft 1024 or 2048)");
     TgParams p{};
     p.tracks = d_tracks;
     p.n_tracks = hb.n_tracks;
-    p.total_tiles = hb.total_tiles;
+    p.total_tiles = int(hb.total_pitch / TG_TF);
     p.win = win;
     p.tw1 = plan->d_tg_tw1;
     p.tw2 = plan->d_tg_tw2;
@@ -184,7 +183,7 @@ int run_tempogram(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_t
     const size_t smem = ((size_t(win) * (TG_TF + 1) * 4 + 15) / 16) * 16 + size_t(8) * C::EX * 8 + size_t(15) * C::M * 8 +
                         size_t(16) * C::Q * 8 + 16 * 2 * 4;
     TA_CUDA(cudaFuncSetAttribute(tempogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = std::max(1, std::min(plan->sm_count, hb.total_tiles));
+    const int grid = std::max(1, std::min(plan->sm_count, p.total_tiles));
     tempogram_kernel<<<grid, 512, smem, stream>>>(p);
     count_launch();
     TA_CUDA(cudaGetLastError());
