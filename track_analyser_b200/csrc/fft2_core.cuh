@@ -200,8 +200,12 @@ TA_HD void pass2(C2 (&v)[16], int tid, const float2* __restrict__ tw2, float4* e
     using C = FftCfg<N>;
     const int k1 = tid & 15, n3 = tid >> 4;
     float4* base = ex + k1 * C::P1 + n3;
+    // loads in the order the first radix-4 level consumes them (n0, n0+4, n0+8, n0+12), so that the
+    // butterflies of column n0 can issue while the later columns are still in flight
 #pragma unroll
-    for (int n2 = 0; n2 < 16; ++n2) v[n2] = unpack(base[n2 * C::Q]);
+    for (int n0 = 0; n0 < 4; ++n0)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[n0 + 4 * q] = unpack(base[(n0 + 4 * q) * C::Q]);
     dft16(v);
     base[0] = pack(v[0]);
 #pragma unroll

@@ -1,22 +1,25 @@
 // K5 + K6: one pass over the PCM for everything that is computed in the time domain.
 //
 //   K5  BS.1770 K-weighting (pyloudnorm.Meter.integrated_loudness, loudness.py:60-61):
-//       two cascaded biquads evaluated as a parallel linear-recurrence scan in
-//       float64 -- each thread runs the direct-form-II-transposed recurrence over
-//       8 consecutive samples from zero state, the (z0,z1) end states are combined
-//       by a Kogge-Stone warp scan with precomputed powers of the 2x2 transition
-//       matrix, warp totals are chained through shared memory, and the zero-input
-//       response of the true start state is added back.  The stage-1 output is
-//       rounded to float32 before stage 2 and the stage-2 output before squaring,
-//       exactly where scipy.signal.lfilter's float64 result is stored back into
-//       pyloudnorm's float32 working copy.  Chunks of `cs` samples are independent
-//       CTAs: each warms the filters up over the preceding HALO samples from zero
-//       state (the slowest pole pair has |p| = 0.9946; after 8192 samples the
-//       truncation error is below 1e-15 of the state).
-//   K6  mid/side/L/R moments (stereo.py:62-83, loudness.py:118) and hop-granule
-//       sums of mono^2 for the centred RMS frames (loudness.py:30-42).
+//       two cascaded biquads evaluated as a parallel linear-recurrence scan in float64.
+//       Every WARP owns a contiguous chunk of one track and streams through it 256 samples
+//       at a time (8 per lane): each lane runs the direct-form-II-transposed recurrence over
+//       its 8 samples from zero state, the (z0,z1) end states are combined by a Kogge-Stone
+//       warp scan with precomputed powers of the 2x2 transition matrix, and the zero-input
+//       response of the true start state (previous lanes' end state + A^(8*lane) * carry) is
+//       added back with precomputed response vectors -- 16 independent DFMAs instead of a
+//       second dependent recurrence.  No shared memory, no block barrier: the carry lives in
+//       registers.  The stage-1 output is rounded to float32 precision before stage 2 and the
+//       stage-2 output before squaring, exactly where scipy.signal.lfilter's float64 result is
+//       stored back into pyloudnorm's float32 working copy; the rounding is a Veltkamp split
+//       (3 DFMA-class ops) because float<->double conversions run at 1/8 of the DFMA rate.
+//       Chunks are independent: each warms the filters up over the preceding HALO samples
+//       from zero state (the slowest pole pair has |p| = 0.9946; n*r^n < 1e-10 after 6144).
+//   K6  mid/side/L/R moments (stereo.py:62-83, loudness.py:118) and hop-granule sums of mono^2
+//       for the centred RMS frames (loudness.py:30-42): float32 partial sums over a lane's 8
+//       samples, accumulated in float64.
 //   finalize: gating-block energies z_j, absolute/relative gates -> LUFS, RMS frames.
-// HBM-bound target: algorithmic bytes 4*C*N read per track; FP64 work ~33 DFMA/sample.
+// HBM-bound target: algorithmic bytes 4*C*N read per track; FP64 work ~27 DFMA/sample.
 #include <cmath>
 #include <numeric>
 
@@ -24,31 +27,30 @@
 
 namespace ta {
 
-static constexpr int TD_THREADS = 256;
-static constexpr int TD_SEG = 8;                       // samples per thread per iteration
-static constexpr int TD_ITER = TD_THREADS * TD_SEG;    // 2048 samples per iteration
-#ifndef TD_MIN_BLOCKS
-#define TD_MIN_BLOCKS 2
-#endif
-static constexpr int TD_MAXG = 1024;                   // granule accumulators per set per CTA
+static constexpr int TD_SEG = 8;                 // samples per lane per step
+static constexpr int TD_STEP = 32 * TD_SEG;      // samples per warp per step
+static constexpr int TD_WARPS = 4;               // warps per CTA
+static constexpr int TD_THREADS = 32 * TD_WARPS;
 
 struct Mat2 {
     double m00, m01, m10, m11;
 };
 
-struct StageConst {
-    double b0, b1, b2, a1, a2;
-    Mat2 P[5];      // A^(8*2^d), d = 0..4 : Kogge-Stone steps inside a warp
-    Mat2 W;         // A^256 : one warp
-    Mat2 AL[32];    // A^(8*lane)
+// Uniform per-stage constants; passed by value so that they are read as constant-bank operands.
+struct StageU {
+    double b0, b1, b2, na1, na2;
+    Mat2 P[5];            // A^(8*2^d), d = 0..4: Kogge-Stone steps inside the warp
+    Mat2 W;               // A^256: one warp step
+    double H0[TD_SEG];    // zero-input response y_i for start state (1, 0): (A^i)[0][0]
+    double H1[TD_SEG];    //                          and for (0, 1): (A^i)[0][1]
 };
 
 struct TdParams {
     const TrackDesc* tracks;
     int n_tracks;
     int total_chunks;
-    int cs;        // chunk samples (multiple of TD_ITER)
-    int halo;      // warm-up samples before each chunk (multiple of TD_ITER)
+    int cs;        // chunk samples per warp (multiple of TD_STEP)
+    int halo;      // warm-up samples before each chunk (multiple of TD_STEP)
     int stereo;
     int g_k, g_m, g_s;            // granule sizes: K-weighted, momentary hop, short-term hop
     int pitch_k, pitch_m, pitch_s;
@@ -56,7 +58,8 @@ struct TdParams {
     double* gran_m;
     double* gran_s;
     double* moments;              // [n_tracks][8]
-    StageConst stage[2];          // by value (kernel parameter space): no cross-plan races
+    const double* lane_pow;       // [2 stages][32 lanes][4]: A^(8*lane)
+    StageU stage[2];
 };
 
 __host__ __device__ inline Mat2 matmul(const Mat2& a, const Mat2& b) {
@@ -69,32 +72,29 @@ __device__ __forceinline__ void matvec_add(const Mat2& M, double x0, double x1, 
     y1 = fma(M.m10, x0, fma(M.m11, x1, y1));
 }
 
-// Stage constants as laid out in shared memory (copied once per CTA: reading the by-value kernel
-// parameter block through LDC at ~70 distinct addresses thrashed the constant cache -- profiles/r1).
-struct StageSm {
-    double b0, b1, b2, a1, a2, pad;
-    Mat2 P[5];
-    Mat2 W;
-    double al[4][32];  // A^(8*lane), one row per matrix element: conflict-free lane-indexed reads
-};
+// y rounded to 24 significant bits (round to nearest) without leaving the FP64 pipe: Veltkamp split with
+// s = 29.  Equals double(float(y)) for every y in float32's normal range except exact ties, which cannot
+// change any sum at the tolerances of this path.
+__device__ __forceinline__ double round_f32(double y) {
+    const double c = y * 536870913.0;  // 2^29 + 1
+    return c - (c - y);
+}
 
-// One biquad stage over the thread's TD_SEG samples; x is replaced by the filter output (double).
-// carry0/carry1: filter state at the start of this iteration (updated to the state at its end).
-__device__ __forceinline__ void biquad_stage(const StageSm& c, double (&x)[TD_SEG], double& carry0,
-                                             double& carry1, double2* wt /* [8] warp totals */, int lane, int warp) {
-    // 1. zero-state response
-    const double b0 = c.b0, b1 = c.b1, b2 = c.b2, na1 = -c.a1, na2 = -c.a2;
+// One biquad stage over the lane's TD_SEG samples, part 1: zero-state response and the warp-inclusive scan
+// of end states.  x is replaced by the zero-state output; (e0, e1) is the state after this lane's segment
+// given a zero state at the start of the warp's 256-sample block.
+__device__ __forceinline__ void stage_zero_state(const StageU& c, double (&x)[TD_SEG], double& e0, double& e1, int lane) {
     double z0 = 0.0, z1 = 0.0;
 #pragma unroll
     for (int i = 0; i < TD_SEG; ++i) {
         const double xi = x[i];
-        const double y = fma(b0, xi, z0);
-        z0 = fma(na1, y, fma(b1, xi, z1));
-        z1 = fma(na2, y, b2 * xi);
+        const double y = fma(c.b0, xi, z0);
+        z0 = fma(c.na1, y, fma(c.b1, xi, z1));
+        z1 = fma(c.na2, y, c.b2 * xi);
         x[i] = y;
     }
-    // 2. inclusive scan of end states inside the warp
-    double e0 = z0, e1 = z1;
+    e0 = z0;
+    e1 = z1;
 #pragma unroll
     for (int d = 0; d < 5; ++d) {
         const int o = 1 << d;
@@ -102,37 +102,22 @@ __device__ __forceinline__ void biquad_stage(const StageSm& c, double (&x)[TD_SE
         const double p1 = __shfl_up_sync(0xffffffffu, e1, o);
         if (lane >= o) matvec_add(c.P[d], p0, p1, e0, e1);
     }
-    if (lane == 31) wt[warp] = make_double2(e0, e1);
-    __syncthreads();
-    // 3. chain warp totals from the iteration carry; remember the state at this warp's start
-    double s0 = carry0, s1 = carry1, w0 = 0.0, w1 = 0.0;
+}
+
+// Part 2: add the zero-input response of the true start state and advance the carry (state at the start of
+// the warp's block -> state at its end).
+__device__ __forceinline__ void stage_correct(const StageU& c, const Mat2& al, double (&x)[TD_SEG], double e0, double e1,
+                                              double& carry0, double& carry1, int lane) {
+    double s0 = __shfl_up_sync(0xffffffffu, e0, 1);
+    double s1 = __shfl_up_sync(0xffffffffu, e1, 1);
+    if (lane == 0) { s0 = 0.0; s1 = 0.0; }
+    matvec_add(al, carry0, carry1, s0, s1);
 #pragma unroll
-    for (int ww = 0; ww < TD_THREADS / 32; ++ww) {
-        if (ww == warp) { w0 = s0; w1 = s1; }
-        const double2 t = wt[ww];
-        double n0 = t.x, n1 = t.y;
-        matvec_add(c.W, s0, s1, n0, n1);
-        s0 = n0;
-        s1 = n1;
-    }
-    carry0 = s0;
-    carry1 = s1;
-    // 4. true state at the start of this thread's segment
-    double i0 = __shfl_up_sync(0xffffffffu, e0, 1);
-    double i1 = __shfl_up_sync(0xffffffffu, e1, 1);
-    if (lane == 0) { i0 = 0.0; i1 = 0.0; }
-    {
-        const Mat2 al{c.al[0][lane], c.al[1][lane], c.al[2][lane], c.al[3][lane]};
-        matvec_add(al, w0, w1, i0, i1);
-    }
-    // 5. add the zero-input response
-#pragma unroll
-    for (int i = 0; i < TD_SEG; ++i) {
-        const double yi = i0;
-        x[i] += yi;
-        i0 = fma(na1, yi, i1);
-        i1 = na2 * yi;
-    }
+    for (int i = 0; i < TD_SEG; ++i) x[i] = fma(c.H0[i], s0, fma(c.H1[i], s1, x[i]));
+    double n0 = __shfl_sync(0xffffffffu, e0, 31), n1 = __shfl_sync(0xffffffffu, e1, 31);
+    matvec_add(c.W, carry0, carry1, n0, n1);
+    carry0 = n0;
+    carry1 = n1;
 }
 
 // n / g for n < 2^31 without the ~20-instruction integer divide: double reciprocal + one correction.
@@ -143,79 +128,72 @@ __device__ __forceinline__ unsigned fast_div(unsigned n, unsigned g, double inv_
     return q;
 }
 
-// Running granule sum kept in registers: all lanes of a warp sit in the same granule most of the
-// time, so each thread adds its 8 values locally and the warp reduces + publishes (one shared-memory
-// atomic) only when its granule changes.
+// Running granule sum of a warp: all lanes sit in the same granule most of the time, so each lane adds its
+// partial sum locally and the warp reduces + publishes (one global atomic) only when its granule changes.
 struct GranAcc {
     double acc = 0.0;
     unsigned gid = 0xffffffffu;
 };
 
-__device__ __forceinline__ void gran_flush(GranAcc& a, double* sm_acc, int first_gid, int lane) {
-    if (a.gid == 0xffffffffu) return;  // warp-uniform
-    double v = a.acc;
+__device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0) atomicAdd(&sm_acc[int(a.gid) - first_gid], v);
+    return v;
+}
+
+__device__ __forceinline__ void gran_flush(GranAcc& a, double* gran, int lane) {
+    if (a.gid == 0xffffffffu) return;  // warp-uniform
+    const double v = warp_sum(a.acc);
+    if (lane == 0) atomicAdd(&gran[a.gid], v);
     a.acc = 0.0;
     a.gid = 0xffffffffu;
 }
 
-// Adds the thread's TD_SEG values q[] (sample indices n_first..n_first+7).  `all_ok`: every sample of
-// the warp is inside the chunk (warp-uniform).
-__device__ __forceinline__ void granule_add(GranAcc& a, double* sm_acc, int first_gid, unsigned g, double inv_g, unsigned n_first,
-                                            const float (&q)[TD_SEG], const bool (&ok)[TD_SEG], bool all_ok, int lane) {
-    const unsigned n_warp = n_first - unsigned(lane) * TD_SEG;  // first sample of this warp
-    const unsigned gid_w = fast_div(n_warp, g, inv_g);          // warp-uniform
-    if (all_ok && n_warp + 32 * TD_SEG <= (gid_w + 1) * g) {
+// Adds the lane's TD_SEG values q[] (sample indices n_first .. n_first+7; all lanes call this).
+// `full`: every sample of the warp's block is a real sample (warp-uniform); otherwise n_valid counts them.
+__device__ __forceinline__ void granule_add(GranAcc& a, double* gran, unsigned g, double inv_g, unsigned n_block,
+                                            const double (&q)[TD_SEG], bool full, long long n_samples, int lane) {
+    const unsigned gid_w = fast_div(n_block, g, inv_g);  // granule of the block's first sample (warp-uniform)
+    if (full && n_block + TD_STEP <= (gid_w + 1) * g) {
         if (gid_w != a.gid) {
-            gran_flush(a, sm_acc, first_gid, lane);
+            gran_flush(a, gran, lane);
             a.gid = gid_w;
         }
-        a.acc += (double(q[0]) + double(q[1])) + (double(q[2]) + double(q[3])) +
-                 ((double(q[4]) + double(q[5])) + (double(q[6]) + double(q[7])));
+        a.acc += ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
         return;
     }
-    gran_flush(a, sm_acc, first_gid, lane);
-    const unsigned gid = fast_div(n_first, g, inv_g);
-    const unsigned boundary = (gid + 1) * g;  // first sample index of the next granule
-    double lo = 0.0, hi = 0.0;
-    bool any = false;
+    // slow path (a granule boundary or the end of the track inside this block): per-sample granule index,
+    // one atomic per distinct granule per warp (a block spans at most 1 + TD_STEP/g boundaries)
+    gran_flush(a, gran, lane);
+    const unsigned n_first = n_block + unsigned(lane) * TD_SEG;
+    unsigned gid = gid_w;
+    while (true) {
+        const unsigned lo = gid * g, hi = lo + g;
+        double part = 0.0;
 #pragma unroll
-    for (int i = 0; i < TD_SEG; ++i) {
-        if (ok[i]) {
-            any = true;
-            if (n_first + i < boundary) lo += double(q[i]); else hi += double(q[i]);
+        for (int i = 0; i < TD_SEG; ++i) {
+            const unsigned n = n_first + i;
+            if (n >= lo && n < hi && (long long)n < n_samples) part += q[i];
         }
-    }
-    if (any) {
-        atomicAdd(&sm_acc[int(gid) - first_gid], lo);
-        if (n_first + TD_SEG > boundary) atomicAdd(&sm_acc[int(gid) + 1 - first_gid], hi);
+        part = warp_sum(part);
+        if (lane == 0 && part != 0.0) atomicAdd(&gran[gid], part);
+        if (hi >= n_block + TD_STEP) break;  // warp-uniform
+        ++gid;
     }
 }
 
-__global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(const __grid_constant__ TdParams p) {
-    __shared__ double2 wt[2][TD_THREADS / 32];
-    __shared__ double gacc[3][TD_MAXG];
-    __shared__ double red[TD_THREADS / 32][7];
-    __shared__ StageSm cst[2];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 2) {
-        const StageConst& c = p.stage[tid];
-        StageSm& d = cst[tid];
-        d.b0 = c.b0; d.b1 = c.b1; d.b2 = c.b2; d.a1 = c.a1; d.a2 = c.a2; d.pad = 0.0;
-        for (int i = 0; i < 5; ++i) d.P[i] = c.P[i];
-        d.W = c.W;
+__global__ void __launch_bounds__(TD_THREADS, 4) time_domain_kernel(const __grid_constant__ TdParams p) {
+    const int lane = threadIdx.x & 31;
+    const int gw = blockIdx.x * TD_WARPS + (threadIdx.x >> 5), nw = gridDim.x * TD_WARPS;
+    Mat2 al[2];
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const double* t = p.lane_pow + (s * 32 + lane) * 4;
+        al[s] = {t[0], t[1], t[2], t[3]};
     }
-    if (tid < 64) {  // lane-indexed powers: a divergent constant-bank read, done once per CTA
-        const Mat2 m = p.stage[tid >> 5].AL[tid & 31];
-        StageSm& d = cst[tid >> 5];
-        d.al[0][tid & 31] = m.m00; d.al[1][tid & 31] = m.m01; d.al[2][tid & 31] = m.m10; d.al[3][tid & 31] = m.m11;
-    }
-    __syncthreads();
+    const double inv_k = 1.0 / double(p.g_k), inv_m = 1.0 / double(p.g_m), inv_s = 1.0 / double(p.g_s);
 
-    for (int w = blockIdx.x; w < p.total_chunks; w += gridDim.x) {
-        // locate track
+    for (int w = gw; w < p.total_chunks; w += nw) {
         int lo_t = 0, hi_t = p.n_tracks - 1;
         while (lo_t < hi_t) {
             const int mid = (lo_t + hi_t + 1) >> 1;
@@ -226,20 +204,19 @@ __global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(
         const long long cs0 = (long long)(w - td.chunk_begin) * p.cs;
         const long long ce = min(cs0 + (long long)p.cs, (long long)td.n_samples);
         const long long ws = max(0ll, cs0 - (long long)p.halo);
-        const int fg_k = int(cs0 / p.g_k), fg_m = int(cs0 / p.g_m), fg_s = int(cs0 / p.g_s);
-        for (int i = tid; i < 3 * TD_MAXG; i += TD_THREADS) (&gacc[0][0])[i] = 0.0;
-        __syncthreads();
+        double* gk = p.gran_k ? p.gran_k + size_t(trk) * p.pitch_k : nullptr;
+        double* gm = p.gran_m ? p.gran_m + size_t(trk) * p.pitch_m : nullptr;
+        double* gs = p.gran_s ? p.gran_s + size_t(trk) * p.pitch_s : nullptr;
 
         const float* __restrict__ L = td.ch0;
         const float* __restrict__ R = td.ch1;
         const bool vec = ((reinterpret_cast<uintptr_t>(L) & 15) == 0) && (!p.stereo || (reinterpret_cast<uintptr_t>(R) & 15) == 0);
         double c10 = 0, c11 = 0, c20 = 0, c21 = 0;  // carries of stage 1 / stage 2
         GranAcc ga_k, ga_m, ga_s;
-        const double inv_k = 1.0 / double(p.g_k), inv_m = 1.0 / double(p.g_m), inv_s = 1.0 / double(p.g_s);
         double sL = 0, sR = 0, sLL = 0, sRR = 0, sLR = 0, sMM = 0, sSS = 0;
 
-        for (long long n0 = ws; n0 < ce; n0 += TD_ITER) {
-            const long long nf = n0 + (long long)tid * TD_SEG;
+        for (long long n0 = ws; n0 < ce; n0 += TD_STEP) {
+            const long long nf = n0 + (long long)lane * TD_SEG;
             float l[TD_SEG], r[TD_SEG];
             if (vec && nf + TD_SEG <= td.n_samples) {
                 const float4 a = __ldg(reinterpret_cast<const float4*>(L + nf));
@@ -258,89 +235,94 @@ __global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(
                     r[i] = (in && p.stereo) ? __ldg(R + nf + i) : 0.f;
                 }
             }
-            // ---- raw-sample statistics first, so l/r/mono are dead before the filter stages ----
-            const bool warm = n0 + TD_ITER <= cs0;  // warm-up iteration: nothing is accumulated (CTA-uniform)
-            const long long nw = n0 + (long long)warp * 32 * TD_SEG;
-            const bool all_ok = nw >= cs0 && nw + 32 * TD_SEG <= ce;  // warp-uniform
-            const unsigned n32 = unsigned(nf);
-            bool ok[TD_SEG];
+            const bool warm = n0 < cs0;                              // warm-up step: nothing is accumulated
+            const bool full = n0 + TD_STEP <= td.n_samples;          // no sample of this step is past the end
+            const unsigned n32 = unsigned(n0);
             double x[TD_SEG];
             {
-                float qm[TD_SEG];
+                // float32 partial sums over the lane's 8 samples (zero padding past the end adds exact zeros)
+                float mono[TD_SEG];
+                float fL = 0.f, fR = 0.f, fLL = 0.f, fRR = 0.f, fLR = 0.f, fMM = 0.f, fSS = 0.f;
 #pragma unroll
                 for (int i = 0; i < TD_SEG; ++i) {
-                    const float mono = p.stereo ? 0.5f * (l[i] + r[i]) : l[i];
-                    ok[i] = all_ok || ((nf + i >= cs0) && (nf + i < ce));
-                    x[i] = double(mono);
-                    qm[i] = mono * mono;
+                    mono[i] = p.stereo ? 0.5f * (l[i] + r[i]) : l[i];
+                    x[i] = double(mono[i]);
                 }
                 if (!warm) {
 #pragma unroll
                     for (int i = 0; i < TD_SEG; ++i) {
-                        if (!all_ok && !ok[i]) continue;
-                        const double dm = x[i], dl = l[i];
-                        sMM = fma(dm, dm, sMM);
-                        sL += dl;
-                        sLL = fma(dl, dl, sLL);
+                        fMM = fmaf(mono[i], mono[i], fMM);
+                        fL += l[i];
+                        fLL = fmaf(l[i], l[i], fLL);
                         if (p.stereo) {
-                            const double dr = r[i], sd = double(0.5f * (l[i] - r[i]));
-                            sR += dr;
-                            sRR = fma(dr, dr, sRR);
-                            sLR = fma(dl, dr, sLR);
-                            sSS = fma(sd, sd, sSS);
+                            const float sd = 0.5f * (l[i] - r[i]);
+                            fR += r[i];
+                            fRR = fmaf(r[i], r[i], fRR);
+                            fLR = fmaf(l[i], r[i], fLR);
+                            fSS = fmaf(sd, sd, fSS);
                         }
                     }
-                    if (p.gran_m) granule_add(ga_m, gacc[1], fg_m, unsigned(p.g_m), inv_m, n32, qm, ok, all_ok, lane);
-                    if (p.gran_s) granule_add(ga_s, gacc[2], fg_s, unsigned(p.g_s), inv_s, n32, qm, ok, all_ok, lane);
+                    sMM += double(fMM);
+                    sL += double(fL);
+                    sLL += double(fLL);
+                    if (p.stereo) {
+                        sR += double(fR);
+                        sRR += double(fRR);
+                        sLR += double(fLR);
+                        sSS += double(fSS);
+                    }
+                    if (gm || gs) {
+                        double qm[TD_SEG];
+                        const unsigned gid_m = fast_div(n32, unsigned(p.g_m), inv_m), gid_s = fast_div(n32, unsigned(p.g_s), inv_s);
+                        const bool fast_m = full && n32 + TD_STEP <= (gid_m + 1) * unsigned(p.g_m);
+                        const bool fast_s = full && n32 + TD_STEP <= (gid_s + 1) * unsigned(p.g_s);
+                        if (fast_m && fast_s) {   // common case: one float->double conversion serves both
+                            const double v = double(fMM);
+                            if (gm) {
+                                if (gid_m != ga_m.gid) { gran_flush(ga_m, gm, lane); ga_m.gid = gid_m; }
+                                ga_m.acc += v;
+                            }
+                            if (gs) {
+                                if (gid_s != ga_s.gid) { gran_flush(ga_s, gs, lane); ga_s.gid = gid_s; }
+                                ga_s.acc += v;
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < TD_SEG; ++i) qm[i] = double(mono[i] * mono[i]);
+                            if (gm) granule_add(ga_m, gm, unsigned(p.g_m), inv_m, n32, qm, full, td.n_samples, lane);
+                            if (gs) granule_add(ga_s, gs, unsigned(p.g_s), inv_s, n32, qm, full, td.n_samples, lane);
+                        }
+                    }
                 }
             }
-            // ---- K-weighting: shelf, float32 round trip, high-pass, float32 round trip ----
-            biquad_stage(cst[0], x, c10, c11, wt[0], lane, warp);
+            // ---- K-weighting: shelf, float32 rounding, high-pass, float32 rounding, squares ----
+            double e0, e1;
+            stage_zero_state(p.stage[0], x, e0, e1, lane);
+            stage_correct(p.stage[0], al[0], x, e0, e1, c10, c11, lane);
 #pragma unroll
-            for (int i = 0; i < TD_SEG; ++i) x[i] = double(float(x[i]));
-            biquad_stage(cst[1], x, c20, c21, wt[1], lane, warp);
-            if (!warm && p.gran_k) {
-                float qk[TD_SEG];
+            for (int i = 0; i < TD_SEG; ++i) x[i] = round_f32(x[i]);
+            stage_zero_state(p.stage[1], x, e0, e1, lane);
+            stage_correct(p.stage[1], al[1], x, e0, e1, c20, c21, lane);
+            if (!warm && gk) {
 #pragma unroll
                 for (int i = 0; i < TD_SEG; ++i) {
-                    const float y = float(x[i]);
-                    qk[i] = y * y;
+                    const double y = round_f32(x[i]);
+                    x[i] = y * y;
                 }
-                granule_add(ga_k, gacc[0], fg_k, unsigned(p.g_k), inv_k, n32, qk, ok, all_ok, lane);
+                granule_add(ga_k, gk, unsigned(p.g_k), inv_k, n32, x, full, td.n_samples, lane);
             }
         }
-        gran_flush(ga_k, gacc[0], fg_k, lane);
-        gran_flush(ga_m, gacc[1], fg_m, lane);
-        gran_flush(ga_s, gacc[2], fg_s, lane);
-        __syncthreads();
-        // flush granules (a granule is shared by at most two chunks -> a + b is order independent)
-        const int ng_k = int((ce - 1) / p.g_k) - fg_k + 1, ng_m = int((ce - 1) / p.g_m) - fg_m + 1,
-                  ng_s = int((ce - 1) / p.g_s) - fg_s + 1;
-        if (ce > cs0) {
-            if (p.gran_k)
-                for (int i = tid; i < ng_k; i += TD_THREADS) atomicAdd(&p.gran_k[size_t(trk) * p.pitch_k + fg_k + i], gacc[0][i]);
-            if (p.gran_m)
-                for (int i = tid; i < ng_m; i += TD_THREADS) atomicAdd(&p.gran_m[size_t(trk) * p.pitch_m + fg_m + i], gacc[1][i]);
-            if (p.gran_s)
-                for (int i = tid; i < ng_s; i += TD_THREADS) atomicAdd(&p.gran_s[size_t(trk) * p.pitch_s + fg_s + i], gacc[2][i]);
-        }
-        // moments
-        if (p.moments) {
+        if (gk) gran_flush(ga_k, gk, lane);
+        if (gm) gran_flush(ga_m, gm, lane);
+        if (gs) gran_flush(ga_s, gs, lane);
+        if (p.moments && ce > cs0) {
             double v[7] = {sL, sR, sLL, sRR, sLR, sMM, sSS};
 #pragma unroll
             for (int k = 0; k < 7; ++k) {
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
-                if (lane == 0) red[warp][k] = v[k];
-            }
-            __syncthreads();
-            if (tid < 7) {
-                double s = 0.0;
-                for (int ww = 0; ww < TD_THREADS / 32; ++ww) s += red[ww][tid];
-                atomicAdd(&p.moments[size_t(trk) * 8 + tid], s);
+                v[k] = warp_sum(v[k]);
+                if (lane == 0) atomicAdd(&p.moments[size_t(trk) * 8 + k], v[k]);
             }
         }
-        __syncthreads();
     }
 }
 
@@ -443,13 +425,21 @@ static Mat2 mat_pow(Mat2 a, long long e) {
     return r;
 }
 
-static StageConst make_stage(const Biquad& b) {
-    StageConst c{};
-    c.b0 = b.b0; c.b1 = b.b1; c.b2 = b.b2; c.a1 = b.a1; c.a2 = b.a2;
+static StageU make_stage(const Biquad& b, double* lane_pow /* [32][4] */) {
+    StageU c{};
+    c.b0 = b.b0; c.b1 = b.b1; c.b2 = b.b2; c.na1 = -b.a1; c.na2 = -b.a2;
     const Mat2 A{-b.a1, 1.0, -b.a2, 0.0};
     for (int d = 0; d < 5; ++d) c.P[d] = mat_pow(A, (long long)TD_SEG << d);
     c.W = mat_pow(A, (long long)TD_SEG * 32);
-    for (int l = 0; l < 32; ++l) c.AL[l] = mat_pow(A, (long long)TD_SEG * l);
+    for (int i = 0; i < TD_SEG; ++i) {
+        const Mat2 ai = mat_pow(A, i);
+        c.H0[i] = ai.m00;
+        c.H1[i] = ai.m01;
+    }
+    for (int l = 0; l < 32; ++l) {
+        const Mat2 m = mat_pow(A, (long long)TD_SEG * l);
+        lane_pow[l * 4 + 0] = m.m00; lane_pow[l * 4 + 1] = m.m01; lane_pow[l * 4 + 2] = m.m10; lane_pow[l * 4 + 3] = m.m11;
+    }
     return c;
 }
 
@@ -477,17 +467,18 @@ static void td_pitches(const ta_plan* plan, const HostBatch& hb, int& g_k, int& 
     ps = int(max_samples / plan->rms_s_hop + 2);
 }
 
+// granule sums (three areas) followed by the 2 x 32 x 4 lane powers of the transition matrices
 size_t td_granule_doubles(const ta_plan* plan, const HostBatch& hb) {
     int g, pk, pm, ps;
     td_pitches(plan, hb, g, pk, pm, ps);
-    return size_t(hb.n_tracks) * (size_t(pk) + pm + ps);
+    return size_t(hb.n_tracks) * (size_t(pk) + pm + ps) + 256;
 }
 
 int time_chunk_samples(const ta_plan* plan, int64_t total_samples) {
-    // aim for >= 4 chunks per SM, chunk in [8192, 65536], multiple of TD_ITER
-    const int64_t target = total_samples / (int64_t(plan->sm_count) * 4) + 1;
-    int64_t cs = ((target + TD_ITER - 1) / TD_ITER) * TD_ITER;
-    cs = std::min<int64_t>(std::max<int64_t>(cs, 8192), 65536);
+    // one chunk per warp; aim for >= 4 chunks per resident warp (16 per SM), chunk in [16384, 131072]
+    const int64_t target = total_samples / (int64_t(plan->sm_count) * 16 * 4) + 1;
+    int64_t cs = ((target + TD_STEP - 1) / TD_STEP) * TD_STEP;
+    cs = std::min<int64_t>(std::max<int64_t>(cs, 16384), 131072);
     return int(cs);
 }
 
@@ -495,7 +486,7 @@ int run_time_domain(const ta_plan* plan, const HostBatch& hb, const Workspace& w
                     cudaStream_t stream) {
     int64_t max_samples = 0;
     for (auto& t : hb.tracks) max_samples = std::max(max_samples, t.n_samples);
-    TA_REQUIRE(max_samples < (int64_t(1) << 31), "tracks longer than 2^31 samples are not supported");
+    TA_REQUIRE(max_samples < (int64_t(1) << 31) - TD_STEP, "tracks longer than 2^31 samples are not supported");
     const bool want_k = out->kw_blocks || out->lufs;
     const bool want_m = out->rms_momentary != nullptr, want_s = out->rms_short != nullptr;
     const int cs = time_chunk_samples(plan, hb.total_samples);
@@ -508,33 +499,33 @@ int run_time_domain(const ta_plan* plan, const HostBatch& hb, const Workspace& w
     td_pitches(plan, hb, p.g_k, p.pitch_k, p.pitch_m, p.pitch_s);
     p.g_m = plan->rms_m_hop;
     p.g_s = plan->rms_s_hop;
-    if (want_k && (p.g_k < 8 || cs / p.g_k + 2 > TD_MAXG)) {
-        set_error("gating-block bounds at this sample rate / block size have no common granule >= 8 samples");
-        return TA_ERR_UNSUPPORTED;
-    }
-    TA_REQUIRE(p.g_m >= 8 && p.g_s >= 8, "RMS hop too small");
-    TA_REQUIRE(cs / p.g_m + 2 <= TD_MAXG && cs / p.g_s + 2 <= TD_MAXG, "RMS hop too small for the chunk size");
-    const size_t need = size_t(hb.n_tracks) * (size_t(p.pitch_k) + p.pitch_m + p.pitch_s);
-    TA_REQUIRE(need <= ws.gran_doubles, "granule workspace too small");
+    TA_REQUIRE(p.g_k >= 1 && p.g_m >= 1 && p.g_s >= 1, "granule sizes must be positive");
+    const size_t gran = size_t(hb.n_tracks) * (size_t(p.pitch_k) + p.pitch_m + p.pitch_s);
+    TA_REQUIRE(gran + 256 <= ws.gran_doubles, "granule workspace too small");
     p.gran_k = want_k ? ws.d_granules : nullptr;
     p.gran_m = want_m ? ws.d_granules + size_t(hb.n_tracks) * p.pitch_k : nullptr;
     p.gran_s = want_s ? ws.d_granules + size_t(hb.n_tracks) * (size_t(p.pitch_k) + p.pitch_m) : nullptr;
     p.moments = out->moments;
-    TA_CUDA(cudaMemsetAsync(ws.d_granules, 0, sizeof(double) * need, stream));
+    TA_CUDA(cudaMemsetAsync(ws.d_granules, 0, sizeof(double) * gran, stream));
     if (p.moments) TA_CUDA(cudaMemsetAsync(p.moments, 0, sizeof(double) * 8 * hb.n_tracks, stream));
 
     // warm-up length: the slowest K-weighting pole pair is the high-pass double pole of radius r = sqrt(a2);
-    // a zero-input response decays like n*r^n, so take the first multiple of TD_ITER with n*r^n < 1e-10.
+    // a zero-input response decays like n*r^n, so take the first multiple of 2048 with n*r^n < 1e-10.
     {
         const double r = std::sqrt(std::fabs(plan->highpass.a2));
-        int n = TD_ITER;
-        while (n < (1 << 22) && double(n) * std::pow(r, double(n)) > 1e-10) n += TD_ITER;
+        int n = 2048;
+        while (n < (1 << 22) && double(n) * std::pow(r, double(n)) > 1e-10) n += 2048;
         p.halo = n;
     }
-    p.stage[0] = make_stage(plan->shelf);
-    p.stage[1] = make_stage(plan->highpass);
+    double lane_pow[256];
+    p.stage[0] = make_stage(plan->shelf, lane_pow);
+    p.stage[1] = make_stage(plan->highpass, lane_pow + 128);
+    double* d_lane_pow = ws.d_granules + gran;
+    TA_CUDA(cudaMemcpyAsync(d_lane_pow, lane_pow, sizeof(lane_pow), cudaMemcpyHostToDevice, stream));
+    p.lane_pow = d_lane_pow;
 
-    const int grid = std::max(1, std::min(hb.total_chunks, plan->sm_count * 8));
+    const int ctas = (hb.total_chunks + TD_WARPS - 1) / TD_WARPS;
+    const int grid = std::max(1, std::min(ctas, plan->sm_count * 4 * 2));
     time_domain_kernel<<<grid, TD_THREADS, 0, stream>>>(p);
     count_launch();
     TA_CUDA(cudaGetLastError());
