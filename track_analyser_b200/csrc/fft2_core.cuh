@@ -216,8 +216,9 @@ TA_HD void pass2(C2 (&v)[16], int tid, const float2* __restrict__ tw2, float4* e
 }
 
 // thread tid: butterflies j = tid + M*b (k1 = j & 15, k2 = j >> 4); v[b*Q + k3] = Z[j + 256*k3].
-// The upper half (k3 >= Q/2) goes back to its slots for the mirror reads of the Hermitian split.
-template <int N>
+// STORE = 1: the upper half (k3 >= Q/2) goes back to its slots for the mirror reads of the Hermitian split
+// of a half spectrum; STORE = 2: every value goes back (full-spectrum mirror reads); STORE = 0: registers only.
+template <int N, int STORE = 1>
 TA_HD void pass3(C2 (&v)[16], int tid, float4* ex) {
     using C = FftCfg<N>;
 #pragma unroll
@@ -228,12 +229,13 @@ TA_HD void pass3(C2 (&v)[16], int tid, float4* ex) {
         for (int n3 = 0; n3 < C::Q; ++n3) v[b * C::Q + n3] = unpack(src[n3]);
     }
     dftq<C::Q>(v);
+    if (STORE == 0) return;
 #pragma unroll
     for (int b = 0; b < C::NB; ++b) {
         const int j = tid + C::M * b;
         float4* dst = ex + Ex<N>::slot(j & 15, j >> 4, 0);
 #pragma unroll
-        for (int k3 = C::Q / 2; k3 < C::Q; ++k3) dst[k3] = pack(v[b * C::Q + k3]);
+        for (int k3 = (STORE == 2 ? 0 : C::Q / 2); k3 < C::Q; ++k3) dst[k3] = pack(v[b * C::Q + k3]);
     }
 }
 

@@ -182,7 +182,10 @@ __device__ __forceinline__ void granule_add(GranAcc& a, double* gran, unsigned g
     }
 }
 
-__global__ void __launch_bounds__(TD_THREADS, 4) time_domain_kernel(const __grid_constant__ TdParams p) {
+#ifndef TD_MIN_BLOCKS
+#define TD_MIN_BLOCKS 3  // 158 registers, no spills: 4.0 ms vs 4.6 ms at 4 blocks/SM with spills (profiles/r1_notes.md)
+#endif
+__global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(const __grid_constant__ TdParams p) {
     const int lane = threadIdx.x & 31;
     const int gw = blockIdx.x * TD_WARPS + (threadIdx.x >> 5), nw = gridDim.x * TD_WARPS;
     Mat2 al[2];
@@ -215,9 +218,9 @@ __global__ void __launch_bounds__(TD_THREADS, 4) time_domain_kernel(const __grid
         GranAcc ga_k, ga_m, ga_s;
         double sL = 0, sR = 0, sLL = 0, sRR = 0, sLR = 0, sMM = 0, sSS = 0;
 
-        for (long long n0 = ws; n0 < ce; n0 += TD_STEP) {
+        // raw samples of the lane's segment at step n0 (zero past the end of the track)
+        auto load_step = [&](long long n0, float (&l)[TD_SEG], float (&r)[TD_SEG]) {
             const long long nf = n0 + (long long)lane * TD_SEG;
-            float l[TD_SEG], r[TD_SEG];
             if (vec && nf + TD_SEG <= td.n_samples) {
                 const float4 a = __ldg(reinterpret_cast<const float4*>(L + nf));
                 const float4 b = __ldg(reinterpret_cast<const float4*>(L + nf) + 1);
@@ -235,6 +238,17 @@ __global__ void __launch_bounds__(TD_THREADS, 4) time_domain_kernel(const __grid
                     r[i] = (in && p.stereo) ? __ldg(R + nf + i) : 0.f;
                 }
             }
+        };
+        float ln[TD_SEG], rn[TD_SEG];  // software pipeline: the next step's samples are in flight during this step
+        load_step(ws, ln, rn);
+        for (long long n0 = ws; n0 < ce; n0 += TD_STEP) {
+            float l[TD_SEG], r[TD_SEG];
+#pragma unroll
+            for (int i = 0; i < TD_SEG; ++i) {
+                l[i] = ln[i];
+                r[i] = rn[i];
+            }
+            if (n0 + TD_STEP < ce) load_step(n0 + TD_STEP, ln, rn);
             const bool warm = n0 < cs0;                              // warm-up step: nothing is accumulated
             const bool full = n0 + TD_STEP <= td.n_samples;          // no sample of this step is past the end
             const unsigned n32 = unsigned(n0);
@@ -525,7 +539,7 @@ int run_time_domain(const ta_plan* plan, const HostBatch& hb, const Workspace& w
     p.lane_pow = d_lane_pow;
 
     const int ctas = (hb.total_chunks + TD_WARPS - 1) / TD_WARPS;
-    const int grid = std::max(1, std::min(ctas, plan->sm_count * 4 * 2));
+    const int grid = std::max(1, std::min(ctas, plan->sm_count * TD_MIN_BLOCKS * 2));
     time_domain_kernel<<<grid, TD_THREADS, 0, stream>>>(p);
     count_launch();
     TA_CUDA(cudaGetLastError());
