@@ -19,6 +19,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "fft2_core.cuh"
 
 namespace ta {
 
@@ -179,43 +180,68 @@ __global__ void __launch_bounds__(256) chroma_fb_kernel(const double* __restrict
     for (int c = 0; c < 12; ++c) dst[c] = float((w[(c + 3) % 12] / len) * octw);  // roll(-3) then float32
 }
 
-__global__ void __launch_bounds__(256) chroma_project_kernel(const TrackDesc* __restrict__ tracks, const float* __restrict__ mag,
+// raw[c, t] = sum_f fb[c, f] * |X[f, t]|^2, then each frame divided by its max: four frames per thread (one
+// 128-bit read of the magnitude row per bin, packed FFMA2 with the filterbank weight as broadcast operand),
+// bins unrolled by four so that four row reads are in flight per thread.
+__global__ void __launch_bounds__(128) chroma_project_kernel(const TrackDesc* __restrict__ tracks, const float* __restrict__ mag,
                                                             const float* __restrict__ fb, float* __restrict__ out, int n_bins) {
+    using namespace p2;
     constexpr int KC = 128;
     __shared__ __align__(16) float wsm[KC * 12];
     const TrackDesc td = tracks[blockIdx.y];
-    if (blockIdx.x * blockDim.x >= td.n_frames) return;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool ok = t < td.n_frames;
+    if (blockIdx.x * blockDim.x * 4 >= td.n_frames) return;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const bool ok = t < td.n_frames;  // rows are padded to a multiple of 32 frames, so t..t+3 stay inside the row
     const float* __restrict__ col = mag + size_t(td.pitch_off) * n_bins + (ok ? t : 0);
     const float* __restrict__ w = fb + size_t(blockIdx.y) * n_bins * 12;
-    float acc[12];
+    float2 acc[12][2];
 #pragma unroll
-    for (int c = 0; c < 12; ++c) acc[c] = 0.f;
+    for (int c = 0; c < 12; ++c) acc[c][0] = acc[c][1] = make_float2(0.f, 0.f);
+    auto accumulate = [&](const float4 m, const float* wk) {
+        const float2 s0 = pmul(make_float2(m.x, m.y), make_float2(m.x, m.y));
+        const float2 s1 = pmul(make_float2(m.z, m.w), make_float2(m.z, m.w));
+        const float4 w0 = *reinterpret_cast<const float4*>(wk);
+        const float4 w1 = *reinterpret_cast<const float4*>(wk + 4);
+        const float4 w2 = *reinterpret_cast<const float4*>(wk + 8);
+        const float ww[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {
+            acc[c][0] = pfmas(s0, ww[c], acc[c][0]);
+            acc[c][1] = pfmas(s1, ww[c], acc[c][1]);
+        }
+    };
     for (int k0 = 0; k0 < n_bins; k0 += KC) {
         const int kn = min(KC, n_bins - k0);
         __syncthreads();
         for (int i = threadIdx.x; i < kn * 12; i += blockDim.x) wsm[i] = w[size_t(k0) * 12 + i];
         __syncthreads();
-        for (int kk = 0; kk < kn; ++kk) {
-            const float m = col[size_t(k0 + kk) * td.ld];
-            const float s = m * m;
-            const float4 w0 = *reinterpret_cast<const float4*>(wsm + kk * 12);
-            const float4 w1 = *reinterpret_cast<const float4*>(wsm + kk * 12 + 4);
-            const float4 w2 = *reinterpret_cast<const float4*>(wsm + kk * 12 + 8);
-            acc[0] = fmaf(w0.x, s, acc[0]); acc[1] = fmaf(w0.y, s, acc[1]); acc[2] = fmaf(w0.z, s, acc[2]); acc[3] = fmaf(w0.w, s, acc[3]);
-            acc[4] = fmaf(w1.x, s, acc[4]); acc[5] = fmaf(w1.y, s, acc[5]); acc[6] = fmaf(w1.z, s, acc[6]); acc[7] = fmaf(w1.w, s, acc[7]);
-            acc[8] = fmaf(w2.x, s, acc[8]); acc[9] = fmaf(w2.y, s, acc[9]); acc[10] = fmaf(w2.z, s, acc[10]); acc[11] = fmaf(w2.w, s, acc[11]);
+        int kk = 0;
+        for (; kk + 4 <= kn; kk += 4) {
+            float4 m[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) m[u] = __ldg(reinterpret_cast<const float4*>(col + size_t(k0 + kk + u) * td.ld));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) accumulate(m[u], wsm + (kk + u) * 12);
         }
+        for (; kk < kn; ++kk) accumulate(__ldg(reinterpret_cast<const float4*>(col + size_t(k0 + kk) * td.ld)), wsm + kk * 12);
     }
     if (!ok) return;
-    float mx = 0.f;
+    float res[12][4];
+    float mx[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int c = 0; c < 12; ++c) mx = fmaxf(mx, fabsf(acc[c]));
-    const float len = (mx < 1.1754943508222875e-38f) ? 1.0f : mx;
+    for (int c = 0; c < 12; ++c) {
+        res[c][0] = acc[c][0].x; res[c][1] = acc[c][0].y; res[c][2] = acc[c][1].x; res[c][3] = acc[c][1].y;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) mx[q] = fmaxf(mx[q], fabsf(res[c][q]));
+    }
+    float len[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) len[q] = (mx[q] < 1.1754943508222875e-38f) ? 1.0f : mx[q];
     float* dst = out + size_t(td.pitch_off) * 12 + t;
 #pragma unroll
-    for (int c = 0; c < 12; ++c) dst[size_t(c) * td.ld] = acc[c] / len;
+    for (int c = 0; c < 12; ++c)
+        *reinterpret_cast<float4*>(dst + size_t(c) * td.ld) =
+            make_float4(res[c][0] / len[0], res[c][1] / len[1], res[c][2] / len[2], res[c][3] / len[3]);
 }
 
 // workspace layout helpers ----------------------------------------------------------------
@@ -292,7 +318,9 @@ int run_chroma(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_trac
                                                                                       double(plan->desc.sample_rate));
     count_launch();
     TA_CUDA(cudaGetLastError());
-    chroma_project_kernel<<<gf, 256, 0, stream>>>(d_tracks, mag, fb, chroma, plan->n_bins);
+    TA_REQUIRE((reinterpret_cast<uintptr_t>(mag) & 15) == 0 && (reinterpret_cast<uintptr_t>(chroma) & 15) == 0,
+               "magnitude and chroma buffers must be 16-byte aligned");
+    chroma_project_kernel<<<dim3((hb.max_frames + 511) / 512, hb.n_tracks), 128, 0, stream>>>(d_tracks, mag, fb, chroma, plan->n_bins);
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TA_OK;
