@@ -126,6 +126,70 @@ def test_config5_shape_4096_256_mels():
     np.testing.assert_allclose(res["centroid"], o["centroid"], rtol=RTOL, atol=1e-3)
 
 
+def test_config5_batch_4096_hop256_256_mels_with_chroma():
+    """BASELINE configs[4] shape (n_fft 4096, hop 256, 256 mels + chroma) on a ragged stereo batch."""
+    sr = 44_100
+    tracks = [synth.synth_track(50 + i, 3.0 + 1.7 * i, sr, 2) for i in range(3)]
+    outs = ("magnitude", "mel", "onset_env", "autocorr", "ltas", "centroid", "rolloff_bin", "band_energy", "chroma", "tuning",
+            "tempogram")
+    res = engine.analyse_batch(plan_for(sr, 4096, 256, 256), tracks, outs)
+    for r, x in zip(res, tracks):
+        o = oracle_outputs(x, sr, 4096, 256, 256)
+        assert pass_rate(r["magnitude"], o["magnitude"]) >= 0.99999
+        np.testing.assert_allclose(r["mel"], o["mel"], rtol=RTOL, atol=ATOL * float(o["mel"].max()))
+        np.testing.assert_allclose(r["onset_env"], o["onset_env"], rtol=RTOL, atol=5e-6)
+        np.testing.assert_allclose(r["autocorr"], o["autocorr"], rtol=RTOL, atol=1e-6 * max(1.0, float(o["autocorr"][0])))
+        np.testing.assert_allclose(r["ltas"], o["ltas"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(r["centroid"], o["centroid"], rtol=RTOL, atol=1e-3)
+        freqs = np.fft.rfftfreq(4096, 1.0 / sr)
+        assert np.mean(freqs[r["rolloff_bin"]] == o["rolloff"]) >= 0.995
+        ref_chroma, tuning = olr.chroma_stft(o["mono"], sr, n_fft=4096, hop_length=256, return_tuning=True)
+        assert r["tuning"] == pytest.approx(tuning, abs=1e-12)
+        np.testing.assert_allclose(r["chroma"], ref_chroma, rtol=RTOL, atol=2e-6)
+        np.testing.assert_allclose(r["tempogram"], olr.tempogram(onset_envelope=o["onset_env"], sr=sr, hop_length=256),
+                                   rtol=RTOL, atol=5e-6)
+        w = pstereo.width_from_band_energy(r["band_energy"], freqs, r.n_frames, None, sr)
+        ref = ofe.frequency_dependent_width(np.asarray(x, np.float32), sr, n_fft=4096, hop_length=256)
+        for k in ("low", "mid", "high"):
+            assert w[k] == pytest.approx(ref[k], rel=RTOL, abs=ATOL)
+
+
+def test_config4_sixty_minute_48k_track():
+    """BASELINE configs[3]: one 60-minute 48 kHz stereo track (T = 337 501 frames, 2^20-point autocorrelation,
+    172.8 M-sample K-weighting scan).  The oracle runs on what it can finish in seconds: the loudness path on the
+    whole signal, the STFT/mel on an interior slice, and K3/K4 re-derived from the GPU's own mel / envelope."""
+    sr = 48_000
+    base = synth.synth_track(7, 60.0, sr, 2)
+    gains = (0.35 + 0.6 * np.abs(np.sin(0.7 * np.arange(60)))).astype(np.float32)
+    x = np.concatenate([g * base for g in gains], axis=1)
+    del base
+    assert x.shape == (2, 172_800_000)
+    outs = ("mel", "onset_env", "autocorr", "lufs", "kw_blocks", "moments", "rms_momentary", "ltas")
+    r = engine.analyse_batch(plan_for(sr), [x], outs)[0]
+    assert r.n_frames == 337_501
+    mono = np.mean(x, axis=0)
+    # K5/K6 on the whole signal
+    assert abs(r["lufs"] - opl.integrated_loudness(mono, sr)) < 0.01
+    kw = opl.block_energies(mono, sr)
+    assert kw.shape == r["kw_blocks"].shape == (35_997,)
+    np.testing.assert_allclose(r["kw_blocks"], kw, rtol=RTOL, atol=1e-12)
+    np.testing.assert_allclose(pstereo.mid_side_from_moments(r["moments"]), ofe.mid_side_rms(x), rtol=RTOL, atol=ATOL)
+    # K1 on an interior slice: frames whose window lies inside the slice are identical to the long track's
+    a, n_sl = 1_000 * 512 * 100, 20 * sr
+    sl = mono[a: a + n_sl]
+    mag = np.abs(olr.stft(sl, 2048, 512))
+    mel = np.einsum("ft,mf->mt", mag**2, olr.filters_mel(sr, 2048), optimize=True)
+    t_off = a // 512
+    inner = slice(3, mel.shape[1] - 3)
+    got = r["mel"][:, t_off + inner.start: t_off + inner.stop]
+    np.testing.assert_allclose(got, mel[:, inner], rtol=RTOL, atol=ATOL * float(mel.max()))
+    # K3 and K4 at full length from the GPU's own mel / envelope
+    env = olr.onset_strength(S=olr.power_to_db(r["mel"]), sr=sr, hop_length=512)
+    np.testing.assert_allclose(r["onset_env"], env, rtol=RTOL, atol=5e-6)
+    ac = olr.autocorrelate(r["onset_env"])
+    np.testing.assert_allclose(r["autocorr"], ac, rtol=RTOL, atol=1e-6 * float(ac[0]))
+
+
 def test_n_fft_1024():
     sr = 22_050
     x = synth.synth_track(9, 3.0, sr, 1)

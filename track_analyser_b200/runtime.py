@@ -72,8 +72,6 @@ def frontend(samples: np.ndarray, sample_rate: int, *, n_fft: int = 2048, hop: i
     if want is None:  # "everything" means everything this plan can produce
         if n_mels == 0:
             outs = tuple(o for o in outs if o not in ("mel", "onset_env", "autocorr", "flux_linear", "tempogram"))
-        if n_fft == 4096:
-            outs = tuple(o for o in outs if o != "tempogram")
     res = engine.analyse_batch(plan, [x], outs)[0]
     if cache is not None:
         cache[key] = res
