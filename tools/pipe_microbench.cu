@@ -17,7 +17,14 @@ __device__ __forceinline__ float2 add2(float2 a, float2 b) {
     return d;
 }
 
-template <int ILP, int MODE>  // 0 FFMA, 1 FFMA2, 2 FADD, 3 FADD2
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    float2 d;
+    asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2,%3}; mov.b64 rb, {%4,%5}; mul.rn.f32x2 rd, ra, rb; mov.b64 {%0,%1}, rd;}"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+
+template <int ILP, int MODE>  // 0 FFMA, 1 FFMA2, 2 FADD, 3 FADD2, 4 FMUL (scalar x2), 5 FMUL2, 6 FMUL2 with broadcast operand
 __global__ void k(float* out, float a, float b, int iters) {
     float2 x[ILP];
 #pragma unroll
@@ -30,6 +37,9 @@ __global__ void k(float* out, float a, float b, int iters) {
             if (MODE == 1) x[i] = fma2(x[i], A, B);
             if (MODE == 2) { x[i].x += B.x; x[i].y += B.y; }
             if (MODE == 3) x[i] = add2(x[i], B);
+            if (MODE == 4) { x[i].x *= A.x; x[i].y *= A.y; }
+            if (MODE == 5) x[i] = mul2(x[i], A);
+            if (MODE == 6) x[i] = mul2(x[i], make_float2(A.x, A.x));
         }
     }
     float s = 0;
@@ -92,14 +102,17 @@ int main() {
     int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     const int iters = 20000;
     printf("clock %d kHz\n", clk);
-    const char* names[4] = {"FFMA (scalar x2)", "FFMA2", "FADD (scalar x2)", "FADD2"};
+    const char* names[7] = {"FFMA (scalar x2)", "FFMA2", "FADD (scalar x2)", "FADD2", "FMUL (scalar x2)", "FMUL2", "FMUL2 (bcast)"};
     for (int warps : {8, 16, 32}) {
-        float ms[4];
+        float ms[7];
         ms[0] = timeit([&] { k<8, 0><<<148, warps * 32>>>(d, 1.0000001f, 1e-9f, iters); });
         ms[1] = timeit([&] { k<8, 1><<<148, warps * 32>>>(d, 1.0000001f, 1e-9f, iters); });
         ms[2] = timeit([&] { k<8, 2><<<148, warps * 32>>>(d, 1.0000001f, 1e-9f, iters); });
         ms[3] = timeit([&] { k<8, 3><<<148, warps * 32>>>(d, 1.0000001f, 1e-9f, iters); });
-        for (int m = 0; m < 4; ++m) {
+        ms[4] = timeit([&] { k<8, 4><<<148, warps * 32>>>(d, 1.0000001f, 1e-9f, iters); });
+        ms[5] = timeit([&] { k<8, 5><<<148, warps * 32>>>(d, 1.0000001f, 1e-9f, iters); });
+        ms[6] = timeit([&] { k<8, 6><<<148, warps * 32>>>(d, 1.0000001f, 1e-9f, iters); });
+        for (int m = 0; m < 7; ++m) {
             const double lane_ops = 148.0 * warps * 32 * 8 * 2.0 * iters;  // fp32 lane-operations
             printf("%-18s warps/SM %2d: %.3f ms  %.1f fp32 lane-ops/clk/SM\n", names[m], warps, ms[m],
                    lane_ops / (ms[m] * 1e-3) / 148 / (clk * 1e3));
