@@ -239,6 +239,58 @@ TA_HD void pass3(C2 (&v)[16], int tid, float4* ex) {
     }
 }
 
+// ---- paired pass 3 (Q <= 8): no exchange for the Hermitian split --------------------------------------
+// A thread transforms NB/2 butterflies A_b = (k1, k2a) with k2a < 8 together with the butterflies B_b that hold
+// the mirror bins: N - (k1 + 16 k2a + 256 k3) = k1m + 16 k2m + 256 (Q-1-k3) with k1m = (16 - k1) & 15 and
+// k2m = (15 - k2a + [k1 == 0]) & 15.  (0, 0) and (0, 8) mirror themselves and are paired with each other
+// (thread 0, pair 0).  Registers: v[b*Q + k3] = A_b, v[(NB/2 + b)*Q + k3] = B_b.
+template <int N>
+struct Pair3 {
+    using C = FftCfg<N>;
+    static_assert(C::NB >= 2, "pairing needs at least two butterflies per thread");
+    static constexpr int HB = C::NB / 2;
+    TA_HD static void ids(int tid, int b, int& k1, int& k2a, int& k1m, int& k2m) {
+        k1 = tid & 15;
+        k2a = (tid >> 4) + (C::M / 16) * b;
+        if (k1 == 0 && k2a == 0) {
+            k1m = 0;
+            k2m = 8;
+        } else {
+            k1m = (16 - k1) & 15;
+            k2m = (15 - k2a + (k1 == 0 ? 1 : 0)) & 15;
+        }
+    }
+    // bins of pair b: side 0 = butterfly A, side 1 = butterfly B
+    TA_HD static int bin(int tid, int b, int side, int k3) {
+        int k1, k2a, k1m, k2m;
+        ids(tid, b, k1, k2a, k1m, k2m);
+        return (side ? k1m + 16 * k2m : k1 + 16 * k2a) + 256 * k3;
+    }
+    // i = 0..7 enumerates the thread's bins below N/2: i = b*Q + side*(Q/2) + k3
+    TA_HD static int owned_bin(int tid, int i) {
+        return bin(tid, i / C::Q, (i % C::Q) / (C::Q / 2), i % (C::Q / 2));
+    }
+};
+
+template <int N>
+TA_HD void pass3_paired(C2 (&v)[16], int tid, const float4* ex) {
+    using C = FftCfg<N>;
+    using P = Pair3<N>;
+#pragma unroll
+    for (int b = 0; b < P::HB; ++b) {
+        int k1, k2a, k1m, k2m;
+        P::ids(tid, b, k1, k2a, k1m, k2m);
+        const float4* sa = ex + Ex<N>::slot(k1, k2a, 0);
+        const float4* sb = ex + Ex<N>::slot(k1m, k2m, 0);
+#pragma unroll
+        for (int n3 = 0; n3 < C::Q; ++n3) {
+            v[b * C::Q + n3] = unpack(sa[n3]);
+            v[(P::HB + b) * C::Q + n3] = unpack(sb[n3]);
+        }
+    }
+    dftq<C::Q>(v);
+}
+
 // Lower-half bins kept by thread tid after pass 3: i = b*(Q/2) + k3 (k3 < Q/2), 8 per thread.
 template <int N>
 TA_HD int kept_bin(int tid, int i) {

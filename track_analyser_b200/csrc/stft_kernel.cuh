@@ -156,8 +156,12 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
     auto flush = [&](int t) {
         if (STEREO && p.band_energy) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                atomicAdd(&p.band_energy[(size_t(t) * 2 + 1) * B + kept_bin<N>(r, i)], double(acc_s[i]));
+            for (int i = 0; i < 8; ++i) {
+                int k;
+                if constexpr (C::NB >= 2) k = Pair3<N>::owned_bin(r, i);
+                else k = kept_bin<N>(r, i);
+                atomicAdd(&p.band_energy[(size_t(t) * 2 + 1) * B + k], double(acc_s[i]));
+            }
             if (r == 0) atomicAdd(&p.band_energy[(size_t(t) * 2 + 1) * B + N / 2], double(acc_s[8]));
         }
 #pragma unroll
@@ -260,33 +264,54 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
             group_barrier(g, M);
             pass2<N>(v, r, tw2s, ex);
             group_barrier(g, M);
-            pass3<N>(v, r, ex);
-            group_barrier(g, M);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int k = kept_bin<N>(r, i);
-                const C2 zk = v[kept_reg<N>(i)];
-                C2 zn = unpack(ex[E::slot_of((N - k) & (N - 1))]);
-                if (i == 0 && r == 0) zn = zk;  // bin 0 mirrors itself
+            // one lower-half bin (row k of the tile) from its spectrum value and its mirror value
+            auto emit = [&](int k, const C2& zk, const C2& zn, float& side_acc) {
                 C2 xa, xb;
                 split_pair(zk, zn, xa, xb);
                 const float2 pa = pfma(xa.re, xa.re, pmul(xa.im, xa.im));
                 const float2 pb = pfma(xb.re, xb.re, pmul(xb.im, xb.im));
                 *reinterpret_cast<float2*>(tile + k * TFP + f) = make_float2(fast_sqrt(pa.x), fast_sqrt(pa.y));
-                if (STEREO) acc_s[i] += pb.x + pb.y;
+                if (STEREO) side_acc += pb.x + pb.y;
                 else *reinterpret_cast<float2*>(tile + k * TFP + f + 2) = make_float2(fast_sqrt(pb.x), fast_sqrt(pb.y));
+            };
+            if constexpr (C::NB >= 2) {
+                // paired pass 3: every mirror bin is in this thread's registers, no exchange for the split
+                using P = Pair3<N>;
+                constexpr int Q = C::Q, HB = P::HB;
+                pass3_paired<N>(v, r, ex);
+                float dump = 0.f;
+#pragma unroll
+                for (int b = 0; b < HB; ++b) {
+                    const bool special = (b == 0 && r == 0);  // (0,0)/(0,8) pair themselves: redone below
+#pragma unroll
+                    for (int k3 = 0; k3 < Q / 2; ++k3) {
+                        emit(P::bin(r, b, 0, k3), v[b * Q + k3], v[(HB + b) * Q + Q - 1 - k3],
+                             special ? dump : acc_s[b * Q + k3]);
+                        emit(P::bin(r, b, 1, k3), v[(HB + b) * Q + k3], v[b * Q + Q - 1 - k3],
+                             special ? dump : acc_s[b * Q + Q / 2 + k3]);
+                    }
+                }
+                if (r == 0) {  // thread 0, pair 0: bins 256*k3 (k3 <= Q/2) mirror inside butterfly (0,0), 128 + 256*k3 inside (0,8)
+#pragma unroll
+                    for (int k3 = 0; k3 < Q / 2; ++k3) {
+                        emit(256 * k3, v[k3], v[(Q - k3) % Q], acc_s[k3]);
+                        emit(128 + 256 * k3, v[HB * Q + k3], v[HB * Q + Q - 1 - k3], acc_s[Q / 2 + k3]);
+                    }
+                    emit(N / 2, v[Q / 2], v[Q / 2], acc_s[8]);
+                }
+            } else {
+                pass3<N>(v, r, ex);
+                group_barrier(g, M);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int k = kept_bin<N>(r, i);
+                    C2 zn = unpack(ex[E::slot_of((N - k) & (N - 1))]);
+                    if (i == 0 && r == 0) zn = v[kept_reg<N>(i)];  // bin 0 mirrors itself
+                    emit(k, v[kept_reg<N>(i)], zn, acc_s[i]);
+                }
+                if (r == 0) emit(N / 2, v[C::Q / 2], v[C::Q / 2], acc_s[8]);  // bin N/2 (thread 0, k3 = Q/2) mirrors itself
             }
-            if (r == 0) {  // bin N/2 (thread 0, butterfly 0, k3 = Q/2) mirrors itself
-                const C2 z = v[C::Q / 2];
-                C2 xa, xb;
-                split_pair(z, z, xa, xb);
-                const float2 pa = pfma(xa.re, xa.re, pmul(xa.im, xa.im));
-                const float2 pb = pfma(xb.re, xb.re, pmul(xb.im, xb.im));
-                *reinterpret_cast<float2*>(tile + (N / 2) * TFP + f) = make_float2(fast_sqrt(pa.x), fast_sqrt(pa.y));
-                if (STEREO) acc_s[8] += pb.x + pb.y;
-                else *reinterpret_cast<float2*>(tile + (N / 2) * TFP + f + 2) = make_float2(fast_sqrt(pb.x), fast_sqrt(pb.y));
-            }
-            group_barrier(g, M);  // mirror reads done before the next slot's pass 1 overwrites the slots
+            group_barrier(g, M);  // pass-3 / mirror reads done before the next slot's pass 1 overwrites the slots
         }
         __syncthreads();
 
