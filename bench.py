@@ -228,7 +228,7 @@ def ours(args, rank, world, local_rank):
     for i in range(nt):
         pcm[i * stride: i * stride + 2 * n].copy_(host_pool[i % pool_n], non_blocking=True)
     batch = engine.DeviceBatch(plan, pcm, np.arange(nt, dtype=np.int64) * stride, np.full(nt, n, dtype=np.int64), 2)
-    bufs = engine.FrontendBuffers(batch, engine.ALL_OUTPUTS)
+    bufs = engine.FrontendBuffers(batch, engine.FRONTEND_OUTPUTS)
     torch.cuda.synchronize()
 
     def barrier():
@@ -264,7 +264,7 @@ def ours(args, rank, world, local_rank):
     chunk = min(args.chunk_tracks, nt)
     del bufs, batch, pcm
     torch.cuda.empty_cache()
-    pipe = engine.HostPipeline(plan, n, 2, chunk, engine.ALL_OUTPUTS)
+    pipe = engine.HostPipeline(plan, n, 2, chunk, engine.FRONTEND_OUTPUTS)
     tracks = [host_pool[i % pool_n] for i in range(nt)]
     sink = []
 

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define TA_ABI_VERSION 1
+#define TA_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define TA_API __attribute__((visibility("default")))
@@ -120,6 +120,8 @@ typedef struct ta_frontend_out {
     float* chroma;         /* [12 * P] chroma_stft, inf-normalised per frame: harmony.py:108,149 (needs magnitude) */
     double* tuning;        /* [n_tracks] estimated tuning in fractions of a bin (librosa.estimate_tuning) */
     float* tempogram;      /* [win * P] autocorrelation tempogram of onset_env: report.py:260 */
+    float* true_peak;      /* [n_tracks] max |y| of the 8x polyphase-oversampled mono signal (linear; dBTP =
+                              20 log10(. + 1e-12)): true_peak_dbtp, analysis/loudness.py:81-97 */
     int32_t kw_pitch;      /* capacity per track of kw_blocks */
     int32_t rms_pitch;     /* capacity per track of rms_momentary / rms_short */
 } ta_frontend_out;
@@ -165,7 +167,9 @@ TA_API int ta_autocorrelate(const ta_plan* plan, const ta_batch* batch, const fl
 /* K5+K6: one pass over the PCM: K-weighting biquad cascade as a chunked linear
  * recurrence scan (float64 state, float32 round trip between stages like
  * scipy.signal.lfilter inside pyloudnorm), gating-block energies, BS.1770 gating,
- * mid/side/LR moments and the centred RMS frames: loudness.py:30-61,118; stereo.py:62-83. */
+ * mid/side/LR moments and the centred RMS frames: loudness.py:30-61,118; stereo.py:62-83; and
+ * (K8) the true peak: scipy.signal.resample_poly(x, 8, 1) + max |.| of loudness.py:81-97, evaluated
+ * exactly but only where the 161-tap interpolator can reach the maximum. */
 TA_API int ta_time_domain(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out,
                    void* workspace, size_t workspace_bytes, void* stream);
 

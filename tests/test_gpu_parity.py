@@ -407,6 +407,57 @@ def test_tempogram_short_track_inside_window():
     np.testing.assert_allclose(r["tempogram"], olr.tempogram(onset_envelope=env, sr=sr), rtol=RTOL, atol=5e-6)
 
 
+# ------------------------------------------------------------------------------ true peak (K8)
+def _tp_db(v):
+    return 20.0 * np.log10(float(v) + 1e-12)
+
+
+@pytest.mark.parametrize("name", ["synth_stereo", "synth_mono_48k", "sine_m18", "square", "impulse", "silence", "tiny", "edge_peak"])
+def test_true_peak_matches_oracle(name):
+    sr = 44_100
+    if name == "synth_stereo":
+        x = synth.synth_track(61, 12.0, sr, 2)
+    elif name == "synth_mono_48k":
+        sr, x = 48_000, synth.synth_track(62, 7.3, 48_000, 1)
+    elif name == "sine_m18":
+        sr, x = 48_000, signals.minus18_sine(48_000)  # reference tests/test_loudness.py:46-55
+    elif name == "square":   # worst case for the screening: every step is a candidate
+        x = np.where(np.arange(3 * sr) % 100 < 50, 0.8, -0.8).astype(np.float32)
+    elif name == "impulse":
+        x = np.zeros(sr, np.float32)
+        x[sr // 3] = -0.7
+    elif name == "silence":
+        x = np.zeros(sr, np.float32)
+    elif name == "tiny":
+        x = signals.sine(440.0, sr, 0.004)  # 176 samples: shorter than one step and than the filter
+    else:  # the largest sample sits on the last position of a 256-sample step, its overshoot in the next one
+        rng = np.random.default_rng(5)
+        x = (0.05 * rng.standard_normal(8 * 256)).astype(np.float32)
+        x[3 * 256 - 1], x[3 * 256] = 0.9, 0.85
+    r = engine.analyse_batch(plan_for(sr), [x], ("true_peak",))[0]
+    mono = np.mean(x, axis=0) if x.ndim == 2 else x
+    ref = ofe.true_peak_dbtp(mono, sr)
+    assert _tp_db(r["true_peak"]) == pytest.approx(ref, abs=1e-4)
+    if name == "sine_m18":
+        assert abs(ref - 20 * np.log10(np.max(np.abs(x)))) < 0.2  # the reference's own tolerance
+
+
+def test_true_peak_in_ragged_batch_and_module_api():
+    from track_analyser_b200.analysis import loudness
+
+    sr = 44_100
+    tracks = [synth.synth_track(70 + i, 3.0 + 2.1 * i, sr, 2) for i in range(3)]
+    res = engine.analyse_batch(plan_for(sr), tracks, ("true_peak", "lufs"))
+    for r, x in zip(res, tracks):
+        assert _tp_db(r["true_peak"]) == pytest.approx(ofe.true_peak_dbtp(np.mean(x, axis=0), sr), abs=1e-4)
+    mono = np.mean(tracks[0], axis=0)
+    assert loudness.true_peak_dbtp(mono, sr) == pytest.approx(ofe.true_peak_dbtp(mono, sr), abs=1e-4)
+    with pytest.raises(ValueError):
+        loudness.true_peak_dbtp(tracks[0], sr)
+    with pytest.raises(NotImplementedError):
+        loudness.true_peak_dbtp(mono, sr, oversample=4)
+
+
 # ------------------------------------------------------------------------------ analyse_track
 def test_analyse_track_pipeline_like_reference():
     from track_analyser_b200 import harmony, pipeline
@@ -441,6 +492,7 @@ def test_analyse_track_pipeline_like_reference():
     k_ref = harmony.key_index(harmony._rank_keys(*harmony._score_keys([ref_chroma])))
     assert k_gpu == k_ref
     assert res.loudness.integrated_lufs == pytest.approx(opl.integrated_loudness(mono, sr), abs=0.01)
+    assert res.loudness.true_peak_dbfs == pytest.approx(ofe.true_peak_dbtp(mono, sr), abs=1e-4)
     assert res.features.ltas.magnitude.shape == (1025,)
     m, s = ofe.mid_side_rms(x)
     assert (res.stereo.mid_rms, res.stereo.side_rms) == pytest.approx((m, s), rel=RTOL)

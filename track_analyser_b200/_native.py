@@ -14,7 +14,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libta_b200.so")
 
-TA_ABI_VERSION = 1
+TA_ABI_VERSION = 2
 TA_OK = 0
 TA_ERR_INVALID = -1
 TA_ERR_CUDA = -2
@@ -77,6 +77,7 @@ class FrontendOut(C.Structure):
         ("chroma", C.c_void_p),
         ("tuning", C.c_void_p),
         ("tempogram", C.c_void_p),
+        ("true_peak", C.c_void_p),
         ("kw_pitch", C.c_int32),
         ("rms_pitch", C.c_int32),
     ]

@@ -2,9 +2,9 @@
 
 ``measure_loudness`` keeps the reference signature (loudness.py:45-78); the
 K-weighting scan, 400 ms gated block energies, BS.1770 gating and the centred RMS
-frames are computed by csrc/timedomain.cu.  ``true_peak_dbtp`` (loudness.py:81-97)
-is outside the section-8a path and still uses SciPy's polyphase
-resampler on the host.
+frames are computed by csrc/timedomain.cu, and ``true_peak_dbtp`` (loudness.py:81-97,
+SURVEY 8f rank 2) by csrc/truepeak.cu: the reference's 8x polyphase resampler evaluated
+exactly, but only where its output can reach the maximum.
 """
 
 from __future__ import annotations
@@ -59,13 +59,10 @@ def true_peak_dbtp(samples: np.ndarray, sample_rate: int, *, oversample: int = 8
     samples = np.asarray(samples, dtype=np.float32)
     if samples.ndim != 1:
         raise ValueError("true_peak_dbtp expects mono audio samples")
-    if oversample == 1:
-        up = samples
-    else:
-        from scipy import signal
-
-        up = signal.resample_poly(samples, oversample, 1)
-    return float(20.0 * np.log10(float(np.max(np.abs(up))) + 1e-12))
+    if oversample != 8:
+        raise NotImplementedError("the device kernel implements the reference's default oversample=8 only")
+    peak = _td(samples, sample_rate, 0.4, ("true_peak",))["true_peak"] if samples.size else 0.0
+    return float(20.0 * np.log10(float(peak) + 1e-12))
 
 
 def analyse_loudness(audio: AudioInput | str, *, seed: int, meter_block_size: float = 0.400) -> LoudnessAnalysis:

@@ -63,6 +63,10 @@ struct ta_plan {
     float2* d_tg_tw1 = nullptr;   // tempogram transform (N = 1024) twiddles and window
     float2* d_tg_tw2 = nullptr;
     float* d_tg_window = nullptr;
+    // true peak (K8): 8 polyphase branches x 21 taps of 8 * firwin(161, 1/8, kaiser 5.0), float32 like scipy
+    float tp_coef[8 * 21];
+    float tp_gain;   // max over branches of sum |c|: |y| <= tp_gain * max |x| over the 21-sample window
+    float tp_floor;  // |y[8q]| >= tp_floor * |x[q]| at the sample of largest magnitude
     // host copies
     std::vector<float> h_window;
     std::vector<float> h_mel_dense;
@@ -97,6 +101,10 @@ struct Workspace {
     size_t fft_elems;
     void* d_chroma;            // chroma_stft scratch (peak lists, filterbanks)
     size_t chroma_bytes;
+    float* d_blk_absmax;       // [n_tracks][blk_pitch] max |mono| per 256-sample step (true-peak screening)
+    uint32_t* d_absmax_bits;   // [n_tracks] float bits of max |mono|
+    int blk_pitch;
+    void* d_tp_begin;          // [n_tracks] int64 first step index per track (true-peak kernel)
     unsigned char* end;
 };
 int stft_tile_frames(int n_fft);

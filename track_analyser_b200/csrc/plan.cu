@@ -194,6 +194,45 @@ static int plan_build(ta_plan* p) {
     double coefs[12];
     biquad_kweight(d.sample_rate, p->shelf, p->highpass, coefs);
 
+    {   // true-peak interpolator: scipy.signal.resample_poly(x, 8, 1) = firwin(161, 1/8, window=("kaiser", 5.0)),
+        // cast to float32 (scipy matches the dtype of x) and scaled by 8; y[8q + ph] = sum_i c[ph][i + 10] * x[q - i]
+        auto bessel_i0 = [](double x) {
+            double s = 1.0, t = 1.0;
+            for (int k = 1; k < 200; ++k) {
+                t *= (x * 0.5) * (x * 0.5) / (double(k) * double(k));
+                s += t;
+                if (t < 1e-18 * s) break;
+            }
+            return s;
+        };
+        const int NT = 161, HL = 80;
+        const double fc = 0.125, beta = 5.0;
+        double h[NT], sum = 0.0;
+        for (int n = 0; n < NT; ++n) {
+            const double m = double(n - HL);
+            const double sinc = (m == 0.0) ? 1.0 : std::sin(PI * fc * m) / (PI * fc * m);
+            const double r = m / double(HL);
+            h[n] = fc * sinc * bessel_i0(beta * std::sqrt(std::max(0.0, 1.0 - r * r))) / bessel_i0(beta);
+            sum += h[n];
+        }
+        float gain = 0.f;
+        for (int ph = 0; ph < 8; ++ph) {
+            float g = 0.f;
+            for (int i = -10; i <= 10; ++i) {
+                const int idx = HL + ph + 8 * i;
+                const float c = (idx >= 0 && idx < NT) ? float(h[idx] / sum) * 8.0f : 0.f;
+                p->tp_coef[ph * 21 + (i + 10)] = c;
+                g += std::fabs(c);
+            }
+            gain = std::max(gain, g);
+        }
+        float others = 0.f;
+        for (int i = -10; i <= 10; ++i)
+            if (i != 0) others += std::fabs(p->tp_coef[i + 10]);
+        p->tp_gain = gain * 1.0001f;                                          // margins cover float32 accumulation
+        p->tp_floor = (std::fabs(p->tp_coef[10]) - others) * 0.9999f;
+    }
+
     // loudness framing (analysis/loudness.py:35-38 and pyloudnorm block bounds)
     auto rms_frame = [&](double seconds) {
         int fl = std::max(1024, int(std::nearbyint(double(d.sample_rate) * seconds)));
@@ -293,6 +332,14 @@ size_t carve_workspace(const ta_plan* plan, const HostBatch& hb, void* base, Wor
     ws.d_fft = reinterpret_cast<double*>(take(sizeof(double) * ws.fft_elems));
     ws.chroma_bytes = chroma_scratch_bytes(plan, hb);
     ws.d_chroma = take(ws.chroma_bytes);
+    {
+        int64_t max_samples = 0;
+        for (auto& t : hb.tracks) max_samples = std::max(max_samples, t.n_samples);
+        ws.blk_pitch = int(max_samples / 256 + 2);
+        ws.d_blk_absmax = reinterpret_cast<float*>(take(sizeof(float) * size_t(hb.n_tracks) * ws.blk_pitch));
+        ws.d_absmax_bits = reinterpret_cast<uint32_t*>(take(sizeof(uint32_t) * hb.n_tracks));
+        ws.d_tp_begin = take(sizeof(long long) * hb.n_tracks);
+    }
     ws.end = p ? p + off : nullptr;
     return off;
 }
@@ -507,7 +554,7 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
                                         ws.d_chroma, ws.chroma_bytes, st)) != TA_OK)
         return rc;
     mark(5);
-    const bool need_td = out->moments || out->kw_blocks || out->lufs || out->rms_momentary || out->rms_short;
+    const bool need_td = out->moments || out->kw_blocks || out->lufs || out->rms_momentary || out->rms_short || out->true_peak;
     if (need_td && (rc = run_time_domain(plan, hb, ws, out, st)) != TA_OK) return rc;
     mark(6);
     return TA_OK;

@@ -59,6 +59,9 @@ struct TdParams {
     double* gran_s;
     double* moments;              // [n_tracks][8]
     const double* lane_pow;       // [2 stages][32 lanes][4]: A^(8*lane)
+    float* blk_absmax;            // [n_tracks][blk_pitch] max |mono| of each 256-sample step (nullable)
+    uint32_t* absmax_bits;        // [n_tracks] float bits of max |mono|
+    int blk_pitch;
     StageU stage[2];
 };
 
@@ -217,6 +220,7 @@ __global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(
         double c10 = 0, c11 = 0, c20 = 0, c21 = 0;  // carries of stage 1 / stage 2
         GranAcc ga_k, ga_m, ga_s;
         double sL = 0, sR = 0, sLL = 0, sRR = 0, sLR = 0, sMM = 0, sSS = 0;
+        float amax = 0.f;  // max |mono| of this chunk (true-peak screening)
 
         // raw samples of the lane's segment at step n0 (zero past the end of the track)
         auto load_step = [&](long long n0, float (&l)[TD_SEG], float (&r)[TD_SEG]) {
@@ -261,6 +265,15 @@ __global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(
                 for (int i = 0; i < TD_SEG; ++i) {
                     mono[i] = p.stereo ? 0.5f * (l[i] + r[i]) : l[i];
                     x[i] = double(mono[i]);
+                }
+                if (!warm && p.blk_absmax) {
+                    float bm = 0.f;
+#pragma unroll
+                    for (int i = 0; i < TD_SEG; ++i) bm = fmaxf(bm, fabsf(mono[i]));
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+                    if (lane == 0) p.blk_absmax[size_t(trk) * p.blk_pitch + size_t(n0 / TD_STEP)] = bm;
+                    amax = fmaxf(amax, bm);
                 }
                 if (!warm) {
 #pragma unroll
@@ -329,6 +342,7 @@ __global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(
         if (gk) gran_flush(ga_k, gk, lane);
         if (gm) gran_flush(ga_m, gm, lane);
         if (gs) gran_flush(ga_s, gs, lane);
+        if (p.blk_absmax && lane == 0 && ce > cs0) atomicMax(&p.absmax_bits[trk], __float_as_uint(amax));
         if (p.moments && ce > cs0) {
             double v[7] = {sL, sR, sLL, sRR, sLR, sMM, sSS};
 #pragma unroll
@@ -458,6 +472,7 @@ static StageU make_stage(const Biquad& b, double* lane_pow /* [32][4] */) {
 }
 
 void kw_block_bounds(const ta_plan* plan, int64_t n_samples, std::vector<int64_t>& lo, std::vector<int64_t>& hi);
+int run_true_peak(const ta_plan* plan, const HostBatch& hb, const Workspace& ws, float* true_peak, cudaStream_t stream);
 
 // Largest granule that divides every gating-block bound of a track of `max_samples` samples.
 int kw_granule_for(const ta_plan* plan, int64_t max_samples) {
@@ -520,6 +535,13 @@ int run_time_domain(const ta_plan* plan, const HostBatch& hb, const Workspace& w
     p.gran_m = want_m ? ws.d_granules + size_t(hb.n_tracks) * p.pitch_k : nullptr;
     p.gran_s = want_s ? ws.d_granules + size_t(hb.n_tracks) * (size_t(p.pitch_k) + p.pitch_m) : nullptr;
     p.moments = out->moments;
+    if (out->true_peak) {
+        p.blk_absmax = ws.d_blk_absmax;
+        p.absmax_bits = ws.d_absmax_bits;
+        p.blk_pitch = ws.blk_pitch;
+        TA_CUDA(cudaMemsetAsync(ws.d_absmax_bits, 0, sizeof(uint32_t) * hb.n_tracks, stream));
+        TA_CUDA(cudaMemsetAsync(out->true_peak, 0, sizeof(float) * hb.n_tracks, stream));
+    }
     TA_CUDA(cudaMemsetAsync(ws.d_granules, 0, sizeof(double) * gran, stream));
     if (p.moments) TA_CUDA(cudaMemsetAsync(p.moments, 0, sizeof(double) * 8 * hb.n_tracks, stream));
 
@@ -543,6 +565,11 @@ int run_time_domain(const ta_plan* plan, const HostBatch& hb, const Workspace& w
     time_domain_kernel<<<grid, TD_THREADS, 0, stream>>>(p);
     count_launch();
     TA_CUDA(cudaGetLastError());
+
+    if (out->true_peak) {
+        int rc = run_true_peak(plan, hb, ws, out->true_peak, stream);
+        if (rc != TA_OK) return rc;
+    }
 
     FinParams f{};
     f.tracks = ws.d_tracks;

@@ -21,8 +21,10 @@ from . import _native as nat
 ALL_OUTPUTS = (
     "magnitude", "mel", "onset_env", "autocorr", "flux_linear", "ltas", "centroid", "rolloff_bin",
     "band_energy", "moments", "kw_blocks", "lufs", "rms_momentary", "rms_short", "frame_max", "chroma", "tuning",
-    "tempogram",
+    "tempogram", "true_peak",
 )
+# SURVEY section 8a (the north-star frontend): what bench.py measures.  true_peak is a section-8f "next" row.
+FRONTEND_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o != "true_peak")
 # the bench / default frontend: everything the per-track analysis consumes except the plot-only tempogram
 CORE_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o != "tempogram")
 DEFAULT_OUTPUTS = tuple(o for o in CORE_OUTPUTS if o != "magnitude")
@@ -187,7 +189,7 @@ class FrontendBuffers:
             "kw_blocks": ((nt, self.kw_pitch), torch.float64), "lufs": ((nt,), torch.float64),
             "rms_momentary": ((nt, self.rms_pitch), torch.float64), "rms_short": ((nt, self.rms_pitch), torch.float64),
             "frame_max": ((P,), torch.float32), "chroma": ((12 * P,), torch.float32), "tuning": ((nt,), torch.float64),
-            "tempogram": ((plan.tempogram_win * P,), torch.float32),
+            "tempogram": ((plan.tempogram_win * P,), torch.float32), "true_peak": ((nt,), torch.float32),
         }
         self.t = {k: torch.empty(shapes[k][0], dtype=shapes[k][1], device=dev) for k in ALL_OUTPUTS if k in outputs}
         self.c_out = nat.FrontendOut()
@@ -263,7 +265,7 @@ def download(batch: DeviceBatch, bufs: FrontendBuffers) -> list[TrackResult]:
                 r.data[k] = h[i, : 1 + ns // plan.rms_frames(plan.meter_block)[1]]
             elif k == "rms_short":
                 r.data[k] = h[i, : 1 + ns // plan.rms_frames(3.0)[1]]
-            elif k == "lufs":
+            elif k in ("lufs", "true_peak"):
                 r.data[k] = float(h[i])
             else:
                 r.data[k] = h[i]
