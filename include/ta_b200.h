@@ -122,6 +122,9 @@ typedef struct ta_frontend_out {
     float* tempogram;      /* [win * P] autocorrelation tempogram of onset_env: report.py:260 */
     float* true_peak;      /* [n_tracks] max |y| of the 8x polyphase-oversampled mono signal (linear; dBTP =
                               20 log10(. + 1e-12)): true_peak_dbtp, analysis/loudness.py:81-97 */
+    float* hpss_harmonic;  /* [P]      sum over bins of librosa.decompose.hpss(magnitude)[0]: structure.py:52,143,213 */
+    float* hpss_percussive;/* [P]      same for the percussive component (structure.py:144,212) */
+    float* hpss_scratch;   /* [B * P]  caller-provided scratch (time-direction medians); required with the two above */
     int32_t kw_pitch;      /* capacity per track of kw_blocks */
     int32_t rms_pitch;     /* capacity per track of rms_momentary / rms_short */
 } ta_frontend_out;
@@ -178,6 +181,12 @@ TA_API int ta_time_domain(const ta_plan* plan, const ta_batch* batch, const ta_f
  * per-frame inf-norm: librosa.feature.chroma_stft at harmony.py:108,149. */
 TA_API int ta_chroma_stft(const ta_plan* plan, const ta_batch* batch, const float* magnitude, const float* frame_max,
                           float* chroma, double* tuning, void* workspace, size_t workspace_bytes, void* stream);
+
+/* K9: per-frame sums of the harmonic and percussive components of librosa.decompose.hpss (31-wide median
+ * filters along time and frequency, soft masks with power 2) on an existing magnitude spectrogram:
+ * analysis/structure.py:52 as consumed at :143-144 and :212-213.  scratch: B * P floats. */
+TA_API int ta_hpss_curves(const ta_plan* plan, const ta_batch* batch, const float* magnitude, float* scratch,
+                          float* harmonic_sum, float* percussive_sum, void* workspace, size_t workspace_bytes, void* stream);
 
 /* K4b: windowed (tempogram_win frames, Hann, centred, inf-normalised) autocorrelation of the onset
  * envelope: librosa.feature.tempogram at report.py:260.  Output rows = lags, (win, T_i) per track. */

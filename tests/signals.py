@@ -51,3 +51,20 @@ def tiny_click(sr=44_100):
         audio[start:start + w.shape[0]] += w[: total - start]
     audio = np.clip(audio, -1.0, 1.0)
     return (np.round(audio * 32767.0) / 32768.0).astype(np.float32)  # PCM16 round trip like the WAV on disk
+
+
+def drums_muted_track(sr=22_050, duration=32.0):
+    """reference tests/test_structure.py:10-27: 110 Hz sine + 0.5 s drum hits muted between 12 s and 20 s."""
+    t = np.linspace(0.0, duration, int(sr * duration), endpoint=False)
+    harmonic = 0.3 * np.sin(2 * np.pi * 110.0 * t)
+    drum_times = np.arange(0.0, duration, 0.5)
+    active = drum_times[(drum_times < 12.0) | (drum_times >= 20.0)]
+    drums = np.zeros_like(t)
+    hit = int(sr * 0.05)
+    env = np.linspace(1.0, 0.0, hit, dtype=np.float32)
+    for tm in active:
+        a = int(tm * sr)
+        b = min(len(drums), a + hit)
+        if b > a:
+            drums[a:b] += env[: b - a]
+    return (harmonic + drums).astype(np.float32), sr, np.arange(0.0, duration, 0.5)

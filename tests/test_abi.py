@@ -18,7 +18,7 @@ def test_library_is_built_and_exports_header_symbols(repo_root):
     assert os.path.exists(_native.LIB_PATH), "run __graft_entry__.build() first"
     lib = ctypes.CDLL(_native.LIB_PATH)
     names = header_symbols(repo_root)
-    assert len(names) >= 16
+    assert len(names) >= 17
     for name in names:
         assert hasattr(lib, name), f"{name} declared in ta_b200.h but not exported"
     assert set(names) == set(_native.SYMBOLS), "binding table and header disagree"
@@ -33,7 +33,7 @@ def test_abi_version_and_error_string():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_native.PlanDesc) == 8 * 4 + 4 * 8
     assert ctypes.sizeof(_native.Batch) == 8 + 3 * 8
-    assert ctypes.sizeof(_native.FrontendOut) == 19 * 8 + 8
+    assert ctypes.sizeof(_native.FrontendOut) == 22 * 8 + 8
 
 
 def test_no_cpu_fallback_without_device():

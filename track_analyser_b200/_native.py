@@ -78,6 +78,9 @@ class FrontendOut(C.Structure):
         ("tuning", C.c_void_p),
         ("tempogram", C.c_void_p),
         ("true_peak", C.c_void_p),
+        ("hpss_harmonic", C.c_void_p),
+        ("hpss_percussive", C.c_void_p),
+        ("hpss_scratch", C.c_void_p),
         ("kw_pitch", C.c_int32),
         ("rms_pitch", C.c_int32),
     ]
@@ -99,6 +102,7 @@ SYMBOLS = {
     "ta_onset_flux": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ta_autocorrelate": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ta_chroma_stft": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ta_hpss_curves": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ta_tempogram": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ta_time_domain": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(FrontendOut), C.c_void_p, C.c_size_t, C.c_void_p]),
 }

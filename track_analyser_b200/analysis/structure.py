@@ -1,21 +1,25 @@
-"""Structural segmentation, frontend half (mirror of ``analysis/structure.py:48-59,190-196``).
+"""Structural segmentation (mirror of the reference's ``analysis/structure.py``).
 
-``structure_frontend`` returns what the reference computes with librosa.stft,
-librosa.feature.melspectrogram, librosa.power_to_db and librosa.onset.onset_strength before its
-HPSS / MFCC / peak-picking host logic (structure.py:52,199-342 -- SURVEY 8f rank 1, not yet on
-the device): the magnitude spectrogram, the mel power spectrogram, log-mel and the spectral
-flux computed on LINEAR mel power in float64 (reference quirk).
+Device side (csrc/): the magnitude spectrogram and mel power spectrogram (structure.py:48-59), the
+spectral flux on linear mel power in float64 (structure.py:195, a reference quirk: SURVEY Appendix B)
+and the per-frame sums of the harmonic and percussive HPSS components (structure.py:52 as consumed at
+:143-144 and :212-213; csrc/hpss.cu).  Host side, on those (13 .. 128) x T arrays and T-length curves:
+the MFCC self-similarity, the novelty mix, peak picking, boundary refinement, beat snapping, labelling
+and classification of structure.py:61-342, restated here with the same decisions.
 """
 
 from __future__ import annotations
 
 from dataclasses import dataclass
-from typing import List
+from typing import List, Sequence, Tuple
 
 import numpy as np
+import scipy.fft
+import scipy.ndimage
 
-from .. import runtime
+from .. import hostlogic, runtime
 from ..utils import AudioInput, seed_everything
+from .beats import BeatAnalysis
 
 
 @dataclass(slots=True)
@@ -42,6 +46,8 @@ class StructureFrontend:
     mel: np.ndarray            # (128, T) float32 power    -- structure.py:53-59
     log_mel: np.ndarray        # (128, T) float64          -- structure.py:194
     spectral_flux: np.ndarray  # (T,) float64              -- structure.py:195-196
+    harmonic_curve: np.ndarray | None = None    # (T,) sum over bins of hpss(magnitude)[0]
+    percussive_curve: np.ndarray | None = None  # (T,) sum over bins of hpss(magnitude)[1]
 
 
 def power_to_db(S: np.ndarray, amin: float = 1e-10, top_db: float = 80.0) -> np.ndarray:
@@ -51,11 +57,167 @@ def power_to_db(S: np.ndarray, amin: float = 1e-10, top_db: float = 80.0) -> np.
     return np.maximum(out, out.max() - top_db) if out.size else out
 
 
-def structure_frontend(audio: AudioInput, *, frame_length: int = 2048, hop_length: int = 512) -> StructureFrontend:
+def structure_frontend(audio: AudioInput, *, frame_length: int = 2048, hop_length: int = 512,
+                       magnitude: bool = True) -> StructureFrontend:
     if not isinstance(audio, AudioInput):
         raise TypeError("analyse_structure expects an AudioInput instance")
+    outs = ("mel", "flux_linear", "hpss_harmonic", "hpss_percussive") + (("magnitude",) if magnitude else ())
     res = runtime.frontend(np.asarray(audio.samples, dtype=np.float32), audio.sample_rate, n_fft=frame_length,
-                           hop=hop_length, outputs=("magnitude", "mel", "flux_linear"))
+                           hop=hop_length, outputs=outs)
     mel64 = np.asarray(res["mel"], dtype=float)
-    return StructureFrontend(magnitude=res["magnitude"], mel=res["mel"], log_mel=power_to_db(mel64 + 1e-9),
-                             spectral_flux=np.asarray(res["flux_linear"], dtype=float))
+    return StructureFrontend(magnitude=res["magnitude"] if "magnitude" in res else None, mel=res["mel"],
+                             log_mel=power_to_db(mel64 + 1e-9), spectral_flux=np.asarray(res["flux_linear"], dtype=float),
+                             harmonic_curve=np.asarray(res["hpss_harmonic"]), percussive_curve=np.asarray(res["hpss_percussive"]))
+
+
+# ------------------------------------------------------------------------------ host logic (structure.py:61-342)
+def _unit_range(curve: np.ndarray) -> np.ndarray:
+    if curve.size == 0:
+        return curve
+    lo, hi = float(np.min(curve)), float(np.max(curve))
+    return np.zeros_like(curve) if hi - lo < 1e-9 else (curve - lo) / (hi - lo)
+
+
+def novelty_curves(log_mel: np.ndarray, spectral_flux: np.ndarray, percussive_curve: np.ndarray, harmonic_curve: np.ndarray,
+                   *, hop_length: int, sample_rate: int, context_seconds: float = 2.0) -> Tuple[np.ndarray, np.ndarray]:
+    """(smoothed combined novelty, normalised energy novelty): structure.py:182-224 from the device curves."""
+    frames = log_mel.shape[1]
+    # librosa.feature.mfcc(S=log_mel, n_mfcc=13): orthonormal DCT-II along the mel axis, first 13 rows
+    mfcc = scipy.fft.dct(np.asarray(log_mel, dtype=float), axis=0, type=2, norm="ortho")[:13]
+    mfcc = scipy.ndimage.gaussian_filter1d(mfcc, sigma=1.0, axis=1)
+    context = max(2, int(round(context_seconds * sample_rate / float(hop_length))))
+    self_similarity = np.zeros(frames, dtype=float)
+    for frame in range(context, frames - context):
+        a = np.mean(mfcc[:, frame - context: frame], axis=1)
+        b = np.mean(mfcc[:, frame: frame + context], axis=1)
+        a = a / (np.linalg.norm(a) + 1e-9)
+        b = b / (np.linalg.norm(b) + 1e-9)
+        self_similarity[frame] = 1.0 - float(np.dot(a, b))
+    perc = np.asarray(percussive_curve) if np.size(percussive_curve) else np.zeros(frames)
+    harm = np.asarray(harmonic_curve) if np.size(harmonic_curve) else np.zeros(frames)
+    ratio = perc / (perc + harm + 1e-9)
+    ratio = scipy.ndimage.gaussian_filter1d(ratio, sigma=max(1.0, 0.5 * sample_rate / float(hop_length)))
+    energy_novelty = _unit_range(np.abs(np.diff(ratio, prepend=ratio[0])))
+    combined = 0.5 * _unit_range(np.asarray(spectral_flux, dtype=float)) + 0.3 * _unit_range(self_similarity) + 0.2 * energy_novelty
+    return scipy.ndimage.gaussian_filter1d(combined, sigma=1.5), energy_novelty
+
+
+def _refine(peaks: np.ndarray, energy_novelty: np.ndarray, radius: int) -> np.ndarray:
+    radius = max(1, radius)
+    out = []
+    for idx in (int(v) for v in peaks):
+        lo, hi = max(0, idx - radius), min(energy_novelty.shape[0], idx + radius + 1)
+        out.append(idx if hi <= lo else lo + int(np.argmax(energy_novelty[lo:hi])))
+    return np.asarray(out, dtype=int)
+
+
+def _space_frames(peaks: np.ndarray, novelty: np.ndarray, min_spacing: int) -> np.ndarray:
+    kept: List[int] = []
+    for idx in (int(v) for v in np.sort(peaks)):
+        if kept and idx - kept[-1] < min_spacing:
+            if novelty[idx] > novelty[kept[-1]]:
+                kept[-1] = idx
+        else:
+            kept.append(idx)
+    return np.asarray(kept, dtype=int)
+
+
+def _space_times(times: Sequence[float], frames: Sequence[int], novelty: np.ndarray, min_seconds: float) -> np.ndarray:
+    times, frames = np.asarray(times, dtype=float), np.asarray(frames, dtype=int)
+    if times.size <= 2:
+        return np.ones(times.shape, dtype=bool)
+    kept = [0]
+    for idx in range(1, len(times) - 1):
+        prev = kept[-1]
+        if times[idx] - times[prev] < min_seconds:
+            if prev != 0 and novelty[frames[idx]] > novelty[frames[prev]]:
+                kept[-1] = idx
+        else:
+            kept.append(idx)
+    kept.append(len(times) - 1)
+    mask = np.zeros(times.shape, dtype=bool)
+    mask[kept] = True
+    return mask
+
+
+def _classify(ratios: Sequence[float], perc: Sequence[float], harm: Sequence[float]) -> List[str]:
+    ratios = np.asarray(ratios, dtype=float)
+    total = np.asarray(perc, dtype=float) + np.asarray(harm, dtype=float)
+    if total.size == 0:
+        return []
+    median = float(np.median(total))
+    out = []
+    for i, (ratio, energy) in enumerate(zip(ratios, total)):
+        if i == 0:
+            out.append("intro")
+        elif i == len(ratios) - 1:
+            out.append("outro")
+        elif energy < 0.5 * median and ratio < 0.35:
+            out.append("breakdown")
+        elif ratio > 0.65 and energy >= 0.75 * median:
+            out.append("drop")
+        elif ratio > 0.45:
+            out.append("groove")
+        elif ratio < 0.35:
+            out.append("breakdown")
+        else:
+            out.append("bridge")
+    return out
+
+
+def boundaries_from_curves(novelty: np.ndarray, energy_novelty: np.ndarray, beat_times: Sequence[float], *, sample_rate: int,
+                           hop_length: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Section boundary frames and times: structure.py:86-130 (peak pick, refine, spacing, beat snapping)."""
+    fps = sample_rate / float(hop_length)
+    min_seconds = 8.0
+    min_frames = max(1, int(round(min_seconds * fps)))
+    peaks = hostlogic.peak_pick(novelty, pre_max=8, post_max=8, pre_avg=32, post_avg=32, delta=np.std(novelty) * 0.4,
+                                wait=min_frames)
+    peaks = _refine(peaks, energy_novelty, int(round(fps * 3.0))) if peaks.size else peaks
+    peaks = _space_frames(peaks, novelty, min_frames) if peaks.size else peaks
+    frames = np.asarray(np.unique(np.concatenate(([0], peaks, [len(novelty) - 1]))), dtype=int)
+    times = hostlogic.frames_to_time(frames, sample_rate, hop_length)
+    if len(beat_times):
+        beats = np.asarray(beat_times)
+        times = np.maximum.accumulate(np.asarray([float(beats[int(np.argmin(np.abs(beats - t)))]) for t in times]))
+    keep = _space_times(times, frames, novelty, min_seconds)
+    return frames[keep], np.asarray(times)[keep]
+
+
+def segments_from_curves(frontend: StructureFrontend, beat_result: BeatAnalysis, *, sample_rate: int, hop_length: int,
+                         duration: float) -> StructureAnalysis:
+    if frontend.mel.size == 0:
+        raise ValueError("not enough values to unpack (expected 2, got 0)")  # the reference's behaviour on empty audio
+    novelty, energy_novelty = novelty_curves(frontend.log_mel, frontend.spectral_flux, frontend.percussive_curve,
+                                             frontend.harmonic_curve, hop_length=hop_length, sample_rate=sample_rate)
+    frames, times = boundaries_from_curves(novelty, energy_novelty, beat_result.beat_times, sample_rate=sample_rate,
+                                           hop_length=hop_length)
+    labels = [chr(ord("A") + i % 26) for i in range(len(frames) - 1)]
+    perc_e, harm_e, ratios, segments = [], [], [], []
+    peak = float(np.max(novelty)) + 1e-9
+    for i, start in enumerate(frames[:-1]):
+        end = frames[i + 1]
+        window = novelty[start:end]
+        pe = float(np.sum(frontend.percussive_curve[start:end], dtype=np.float64))
+        he = float(np.sum(frontend.harmonic_curve[start:end], dtype=np.float64))
+        perc_e.append(pe)
+        harm_e.append(he)
+        ratios.append(float(pe / (pe + he + 1e-9)))
+        segments.append(StructuralSegment(
+            label=labels[i], category="", start=float(times[i]), end=float(times[i + 1]),
+            confidence=float(np.clip((float(np.mean(window)) if window.size else 0.0) / peak, 0.0, 1.0)),
+            percussive_energy=pe, harmonic_energy=he, percussive_ratio=ratios[-1]))
+    for seg, cat in zip(segments, _classify(ratios, perc_e, harm_e)):
+        seg.category = cat
+    return StructureAnalysis(segments=segments, novelty_curve=novelty.tolist())
+
+
+def analyse_structure(audio: AudioInput | str, beat_result: BeatAnalysis, *, seed: int, frame_length: int = 2048,
+                      hop_length: int = 512) -> StructureAnalysis:
+    """Detect structural boundaries (reference signature: structure.py:34-41)."""
+    if not isinstance(audio, AudioInput):
+        raise TypeError("analyse_structure expects an AudioInput instance")
+    seed_everything(seed)
+    fe = structure_frontend(audio, frame_length=frame_length, hop_length=hop_length, magnitude=False)
+    return segments_from_curves(fe, beat_result, sample_rate=audio.sample_rate, hop_length=hop_length,
+                                duration=float(audio.duration))

@@ -314,6 +314,8 @@ size_t chroma_scratch_bytes(const ta_plan* plan, const HostBatch& hb);
 int run_chroma(const ta_plan*, const HostBatch&, const TrackDesc*, const float* mag, const float* frame_max, float* chroma,
                double* tuning, void* scratch, size_t scratch_bytes, cudaStream_t);
 int run_tempogram(const ta_plan*, const HostBatch&, const TrackDesc*, const float* env, float* out, cudaStream_t);
+int run_hpss(const ta_plan*, const HostBatch&, const TrackDesc*, const float* mag, float* scratch, float* harm_sum, float* perc_sum,
+             cudaStream_t);
 
 size_t carve_workspace(const ta_plan* plan, const HostBatch& hb, void* base, Workspace& ws) {
     unsigned char* p = reinterpret_cast<unsigned char*>(base);
@@ -518,6 +520,16 @@ int ta_tempogram(const ta_plan* plan, const ta_batch* batch, const float* onset_
     return run_tempogram(plan, hb, ws.d_tracks, onset_env, tempogram, st);
 }
 
+int ta_hpss_curves(const ta_plan* plan, const ta_batch* batch, const float* magnitude, float* scratch, float* harmonic_sum,
+                   float* percussive_sum, void* workspace, size_t workspace_bytes, void* stream) {
+    HostBatch hb;
+    Workspace ws;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = prepare(plan, batch, workspace, workspace_bytes, st, hb, ws);
+    if (rc != TA_OK) return rc;
+    return run_hpss(plan, hb, ws.d_tracks, magnitude, scratch, harmonic_sum, percussive_sum, st);
+}
+
 uint64_t ta_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out, void* workspace,
@@ -553,6 +565,13 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
     if (out->chroma && (rc = run_chroma(plan, hb, ws.d_tracks, out->magnitude, out->frame_max, out->chroma, out->tuning,
                                         ws.d_chroma, ws.chroma_bytes, st)) != TA_OK)
         return rc;
+    if (out->hpss_harmonic || out->hpss_percussive) {
+        TA_REQUIRE(out->magnitude && out->hpss_scratch && out->hpss_harmonic && out->hpss_percussive,
+                   "hpss outputs need the magnitude buffer, hpss_scratch and both sum buffers");
+        if ((rc = run_hpss(plan, hb, ws.d_tracks, out->magnitude, out->hpss_scratch, out->hpss_harmonic, out->hpss_percussive,
+                           st)) != TA_OK)
+            return rc;
+    }
     mark(5);
     const bool need_td = out->moments || out->kw_blocks || out->lufs || out->rms_momentary || out->rms_short || out->true_peak;
     if (need_td && (rc = run_time_domain(plan, hb, ws, out, st)) != TA_OK) return rc;

@@ -21,10 +21,11 @@ from . import _native as nat
 ALL_OUTPUTS = (
     "magnitude", "mel", "onset_env", "autocorr", "flux_linear", "ltas", "centroid", "rolloff_bin",
     "band_energy", "moments", "kw_blocks", "lufs", "rms_momentary", "rms_short", "frame_max", "chroma", "tuning",
-    "tempogram", "true_peak",
+    "tempogram", "true_peak", "hpss_harmonic", "hpss_percussive",
 )
-# SURVEY section 8a (the north-star frontend): what bench.py measures.  true_peak is a section-8f "next" row.
-FRONTEND_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o != "true_peak")
+# SURVEY section 8a (the north-star frontend): what bench.py measures.  true_peak and the HPSS curves are
+# section-8f "next" rows.
+FRONTEND_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o not in ("true_peak", "hpss_harmonic", "hpss_percussive"))
 # the bench / default frontend: everything the per-track analysis consumes except the plot-only tempogram
 CORE_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o != "tempogram")
 DEFAULT_OUTPUTS = tuple(o for o in CORE_OUTPUTS if o != "magnitude")
@@ -177,6 +178,8 @@ class FrontendBuffers:
             outputs |= {"magnitude", "frame_max", "chroma"}
         if outputs & {"onset_env", "autocorr", "flux_linear", "tempogram"}:
             outputs.add("mel")
+        if outputs & {"hpss_harmonic", "hpss_percussive"}:
+            outputs |= {"hpss_harmonic", "hpss_percussive", "magnitude"}
         max_ns = int(batch.n_samples.max()) if nt else 0
         self.kw_pitch = max(1, plan.kw_block_count(max_ns))
         self.rms_pitch = 1 + max_ns // plan.rms_frames(plan.meter_block)[1]
@@ -190,11 +193,15 @@ class FrontendBuffers:
             "rms_momentary": ((nt, self.rms_pitch), torch.float64), "rms_short": ((nt, self.rms_pitch), torch.float64),
             "frame_max": ((P,), torch.float32), "chroma": ((12 * P,), torch.float32), "tuning": ((nt,), torch.float64),
             "tempogram": ((plan.tempogram_win * P,), torch.float32), "true_peak": ((nt,), torch.float32),
+            "hpss_harmonic": ((P,), torch.float32), "hpss_percussive": ((P,), torch.float32),
         }
         self.t = {k: torch.empty(shapes[k][0], dtype=shapes[k][1], device=dev) for k in ALL_OUTPUTS if k in outputs}
         self.c_out = nat.FrontendOut()
         for k in ALL_OUTPUTS:
             setattr(self.c_out, k, self.t[k].data_ptr() if k in self.t else None)
+        # device-only scratch of the HPSS kernels (time-direction medians); never copied to the host
+        self.hpss_scratch = torch.empty(B * P, dtype=torch.float32, device=dev) if "hpss_harmonic" in outputs else None
+        self.c_out.hpss_scratch = self.hpss_scratch.data_ptr() if self.hpss_scratch is not None else None
         self.c_out.kw_pitch = self.kw_pitch
         self.c_out.rms_pitch = self.rms_pitch
         self.outputs = outputs
@@ -257,7 +264,8 @@ def download(batch: DeviceBatch, bufs: FrontendBuffers) -> list[TrackResult]:
                 r.data[k] = h[W * po: W * (po + ld)].reshape(W, ld)[:, :T]
             elif k == "tuning":
                 r.data[k] = float(h[i])
-            elif k in ("onset_env", "autocorr", "flux_linear", "centroid", "rolloff_bin", "frame_max"):
+            elif k in ("onset_env", "autocorr", "flux_linear", "centroid", "rolloff_bin", "frame_max", "hpss_harmonic",
+                       "hpss_percussive"):
                 r.data[k] = h[po: po + T]
             elif k == "kw_blocks":
                 r.data[k] = h[i, : plan.kw_block_count(ns)]

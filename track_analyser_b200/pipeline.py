@@ -3,9 +3,9 @@
 ``TrackAnalysisResult`` keeps the reference's field names and order (pipeline.py:17-29) and
 ``analyse_track`` its signature and stage order (pipeline.py:32-120).  One ``frontend_session``
 spans the call, so the >= 11 identical STFT requests of the reference become one
-fused GPU run per distinct (buffer, n_fft, hop).  ``structure`` and ``harmonic`` hold the GPU
-frontend outputs of those stages (``StructureFrontend`` / ``HarmonyFrontend``): the reference's
-HPSS-, MFCC- and chroma_cqt-based host logic behind them is outside section 8a.
+fused GPU run per distinct (buffer, n_fft, hop).  ``structure`` is the reference's ``StructureAnalysis`` (HPSS curves from csrc/hpss.cu, host logic
+restated in analysis/structure.py); ``harmonic`` holds the GPU frontend outputs of the harmony stage
+(``HarmonyFrontend``): the chroma_cqt-based key/chord logic behind it is outside section 8a.
 """
 
 from __future__ import annotations
@@ -48,7 +48,7 @@ def analyse_track(source, *, output_dir: Optional[str | Path] = None, use_stems:
         beat_result = beats.build_beat_analysis(bpm, grid["time"].to_numpy(), audio.sample_rate, grid=grid)
         downbeat_result = beats.analyse_downbeats(audio, beat_result, seed=seed)
         tick("beats")
-        structure_result = structure.structure_frontend(audio)
+        structure_result = structure.analyse_structure(audio, beat_result, seed=seed)
         tick("structure")
         loudness_result = loudness.analyse_loudness(audio, seed=seed)
         tick("loudness")
