@@ -297,6 +297,13 @@ def ours(args, rank, world, local_rank):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = k1_bytes / (stage[0] * 1e-3) / 1e9
+        traffic = None  # DRAM bytes of one K1 launch from the committed ncu --set full capture of this same command
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_k1_traffic.json")))
+            if args.tracks_per_gpu == 128 and args.seconds == 180.0:
+                traffic = tj["traffic_bytes"]
+        except Exception:
+            pass
         line = {
             "metric": METRIC, "value": world * audio_per_step / (ms_kernel_max * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_kernel_max, "higher_is_better": True,
@@ -304,7 +311,7 @@ def ours(args, rank, world, local_rank):
             "config": workload_config(args, world),
             "stage_ms": {k: float(v) for k, v in zip(engine.STAGE_NAMES, stage)},
             "roofline": {"bound": "hbm", "kernel": "stft_fused_kernel<2048,16,stereo,4>", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "algorithmic_bytes_per_launch": k1_bytes},
             "e2e": {"value": world * audio_per_step / s_e2e_max, "unit": UNIT,
