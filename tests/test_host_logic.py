@@ -107,3 +107,47 @@ def test_wav_reader_round_trip(tmp_path):
     s, sr, meta = tio.load_audio(str(p))
     assert sr == 44_100 and s.shape == (2, 1000) and meta["channels"] == 2
     np.testing.assert_array_equal(s, (x.astype(np.float32) / 32768.0).T)
+
+
+def test_structure_host_logic_on_oracle_curves_like_reference_test():
+    """analysis/structure.py host logic (novelty mix, peak picking, refinement, beat snapping, labelling) fed with the
+    oracle's arrays: the reference's own structure test (tests/test_structure.py) must hold without a GPU."""
+    from track_analyser_b200.analysis import structure
+    from track_analyser_b200.analysis.beats import BeatAnalysis
+
+    samples, sr, beat_times = signals.drums_muted_track()
+    beat = BeatAnalysis(bpm=120.0, beat_times=beat_times.astype(float).tolist(),
+                        beat_frames=(beat_times * sr / 512).astype(int).tolist(), confidence=1.0)
+    mag, mel, log_mel, flux = fe.structure_frontend(samples, sr)
+    harm, perc = lr.hpss(mag)
+    front = structure.StructureFrontend(magnitude=mag, mel=mel, log_mel=log_mel, spectral_flux=flux,
+                                        harmonic_curve=np.sum(harm, axis=0), percussive_curve=np.sum(perc, axis=0))
+    res = structure.segments_from_curves(front, beat, sample_rate=sr, hop_length=512, duration=len(samples) / sr)
+    starts = [s.start for s in res.segments[1:]]
+    assert any(abs(b - 12.0) <= 0.5 for b in starts)
+    assert [s.label for s in res.segments] == [chr(ord("A") + i) for i in range(len(res.segments))]
+    assert res.segments[0].category == "intro" and res.segments[-1].category == "outro"
+    assert all(s.end > s.start for s in res.segments) and res.segments[0].start == 0.0
+    assert all(set(beat_times).__contains__(s.start) for s in res.segments)  # boundaries are snapped to beats
+    for s in res.segments:
+        assert 0.0 <= s.percussive_ratio <= 1.0 and 0.0 <= s.confidence <= 1.0
+    # the segment that starts where the drums drop out is less percussive than the one before it
+    after = next(s for s in res.segments if abs(s.start - 12.0) <= 0.5)
+    assert after.percussive_ratio < res.segments[0].percussive_ratio
+    assert len(res.novelty_curve) == mel.shape[1]
+    empty = structure.StructureFrontend(magnitude=mag[:, :0], mel=mel[:, :0], log_mel=log_mel[:, :0], spectral_flux=flux[:0])
+    with pytest.raises(ValueError):
+        structure.segments_from_curves(empty, beat, sample_rate=sr, hop_length=512, duration=0.0)
+
+
+def test_structure_spacing_helpers():
+    from track_analyser_b200.analysis import structure
+
+    nov = np.array([0.0, 0.9, 0.1, 0.8, 0.2, 1.0, 0.0])
+    np.testing.assert_array_equal(structure._space_frames(np.array([1, 3, 5]), nov, 3), [1, 5])
+    np.testing.assert_array_equal(structure._space_frames(np.array([3, 1]), nov, 1), [1, 3])
+    mask = structure._space_times([0.0, 1.0, 2.0, 20.0, 21.0, 40.0], [0, 1, 3, 4, 5, 6], nov, 8.0)
+    assert mask.tolist() == [True, False, False, True, False, True]
+    assert structure._refine(np.array([3]), np.array([0.0, 0.0, 0.0, 0.1, 0.9, 0.0]), 1).tolist() == [4]
+    assert structure._classify([0.1, 0.7, 0.5, 0.2, 0.4, 0.3], [1, 7, 5, 2, 4, 3], [9, 3, 5, 8, 6, 7]) == [
+        "intro", "drop", "groove", "breakdown", "bridge", "outro"]
