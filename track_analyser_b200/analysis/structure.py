@@ -87,12 +87,13 @@ def novelty_curves(log_mel: np.ndarray, spectral_flux: np.ndarray, percussive_cu
     mfcc = scipy.ndimage.gaussian_filter1d(mfcc, sigma=1.0, axis=1)
     context = max(2, int(round(context_seconds * sample_rate / float(hop_length))))
     self_similarity = np.zeros(frames, dtype=float)
-    for frame in range(context, frames - context):
-        a = np.mean(mfcc[:, frame - context: frame], axis=1)
-        b = np.mean(mfcc[:, frame: frame + context], axis=1)
-        a = a / (np.linalg.norm(a) + 1e-9)
-        b = b / (np.linalg.norm(b) + 1e-9)
-        self_similarity[frame] = 1.0 - float(np.dot(a, b))
+    if frames > 2 * context:
+        # means of every `context`-frame window at once (the reference loops over frames, structure.py:203-210);
+        # window j covers frames [j, j + context): left of frame f is window f - context, right is window f
+        means = np.lib.stride_tricks.sliding_window_view(mfcc, context, axis=1).mean(axis=2)
+        unit = means / (np.linalg.norm(means, axis=0) + 1e-9)
+        f = np.arange(context, frames - context)
+        self_similarity[f] = 1.0 - np.sum(unit[:, f - context] * unit[:, f], axis=0)
     perc = np.asarray(percussive_curve) if np.size(percussive_curve) else np.zeros(frames)
     harm = np.asarray(harmonic_curve) if np.size(harmonic_curve) else np.zeros(frames)
     ratio = perc / (perc + harm + 1e-9)

@@ -44,17 +44,28 @@ def frame_pitch(n_frames: int) -> int:
 
 @dataclass
 class TrackResult:
-    """Per-track host copies of the frontend outputs (numpy, reference shapes)."""
+    """Per-track host copies of the frontend outputs (numpy, reference shapes).
+
+    With a ``loader`` the device buffers stay alive and an output is copied to the host the first time it is
+    asked for (``runtime.frontend_session``: one fused run serves many consumers, most of which want KB-sized
+    outputs, not the 64 MB magnitude)."""
 
     n_samples: int
     n_frames: int
     data: dict = field(default_factory=dict)
+    channels: int = 1
+    loader: object = None   # callable(key) -> numpy value, or None
+    available: tuple = ()
 
     def __getitem__(self, key):
+        if key not in self.data:
+            if self.loader is None or key not in self.available:
+                raise KeyError(key)
+            self.data[key] = self.loader(key)
         return self.data[key]
 
     def __contains__(self, key):
-        return key in self.data
+        return key in self.data or key in self.available
 
 
 class Plan:
@@ -130,15 +141,30 @@ class DeviceBatch:
                                  self.n_samples.ctypes.data_as(C.POINTER(C.c_int64)))
 
 
-def pack_host(tracks: Sequence[np.ndarray], channels: int, pinned: bool = True):
-    """Pack float32 tracks ((C, N) planar or (N,)) into one flat host tensor; offsets are 4-aligned."""
+_staging: dict = {}
+
+
+def _pinned_staging(n: int) -> torch.Tensor:
+    """Reusable pinned host buffer (cudaHostAlloc of tens of MB costs more than the copy it speeds up)."""
+    buf = _staging.get("buf")
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n, 1 << 20), dtype=torch.float32, pin_memory=True)
+        _staging["buf"] = buf
+    return buf[:n]
+
+
+def pack_host(tracks: Sequence[np.ndarray], channels: int, pinned: bool = True, reuse: bool = False):
+    """Pack float32 tracks ((C, N) planar or (N,)) into one flat host tensor; offsets are 4-aligned.
+
+    ``reuse``: stage through one process-wide pinned buffer (the caller must have finished with the previous
+    contents, i.e. synchronise the copy before the next call)."""
     n_samples, offsets, total = [], [], 0
     for t in tracks:
         n = t.shape[-1]
         n_samples.append(n)
         offsets.append(total)
         total += (channels * n + 3) & ~3
-    host = torch.empty(max(total, 4), dtype=torch.float32, pin_memory=pinned)
+    host = _pinned_staging(max(total, 4)) if (pinned and reuse) else torch.empty(max(total, 4), dtype=torch.float32, pin_memory=pinned)
     hv = host.numpy()
     for t, off, n in zip(tracks, offsets, n_samples):
         hv[off: off + channels * n] = np.ascontiguousarray(t, dtype=np.float32).reshape(-1)
@@ -151,9 +177,10 @@ def upload(plan: Plan, tracks: Sequence[np.ndarray]) -> DeviceBatch:
     if len(chans) != 1 or next(iter(chans)) not in (1, 2):
         raise ValueError("a batch must hold tracks that are all mono (N,) / (1, N) or all stereo (2, N)")
     channels = next(iter(chans))
-    host, offsets, n_samples = pack_host(tracks, channels)
+    host, offsets, n_samples = pack_host(tracks, channels, reuse=True)
     dev = torch.empty(host.numel(), dtype=torch.float32, device=f"cuda:{plan.device}")
     dev.copy_(host, non_blocking=True)
+    torch.cuda.current_stream(dev.device).synchronize()  # the shared staging buffer may be refilled right away
     return DeviceBatch(plan, dev, offsets, n_samples, channels)
 
 
@@ -242,53 +269,73 @@ def launch_count() -> int:
     return int(nat.load().ta_launch_count())
 
 
+def _cut(plan: Plan, batch: DeviceBatch, i: int, k: str, h: np.ndarray):
+    """Slice the host copy ``h`` of output ``k`` down to track ``i`` in the reference's shape."""
+    B, M = plan.n_bins, plan.n_mels
+    T, ld, po = int(batch.n_frames[i]), int(batch.pitch[i]), int(batch.pitch_off[i])
+    ns = int(batch.n_samples[i])
+    if k == "magnitude":
+        return h[B * po: B * (po + ld)].reshape(B, ld)[:, :T]
+    if k == "mel":
+        return h[M * po: M * (po + ld)].reshape(M, ld)[:, :T]
+    if k == "chroma":
+        return h[12 * po: 12 * (po + ld)].reshape(12, ld)[:, :T]
+    if k == "tempogram":
+        W = plan.tempogram_win
+        return h[W * po: W * (po + ld)].reshape(W, ld)[:, :T]
+    if k in ("tuning", "lufs", "true_peak"):
+        return float(h[i])
+    if k in ("onset_env", "autocorr", "flux_linear", "centroid", "rolloff_bin", "frame_max", "hpss_harmonic",
+             "hpss_percussive"):
+        return h[po: po + T]
+    if k == "kw_blocks":
+        return h[i, : plan.kw_block_count(ns)]
+    if k == "rms_momentary":
+        return h[i, : 1 + ns // plan.rms_frames(plan.meter_block)[1]]
+    if k == "rms_short":
+        return h[i, : 1 + ns // plan.rms_frames(3.0)[1]]
+    if k == "ltas":
+        return (h[i] / T).astype(np.float32)
+    return h[i]
+
+
 def download(batch: DeviceBatch, bufs: FrontendBuffers) -> list[TrackResult]:
     """Copy results to the host and cut them into per-track numpy arrays of reference shape."""
     plan = batch.plan
     host = {k: v.cpu().numpy() for k, v in bufs.t.items()}
-    B, M = plan.n_bins, plan.n_mels
     out = []
     for i in range(batch.n_tracks):
-        T, ld, po = int(batch.n_frames[i]), int(batch.pitch[i]), int(batch.pitch_off[i])
-        ns = int(batch.n_samples[i])
-        r = TrackResult(n_samples=ns, n_frames=T)
+        r = TrackResult(n_samples=int(batch.n_samples[i]), n_frames=int(batch.n_frames[i]), channels=batch.channels)
         for k, h in host.items():
-            if k == "magnitude":
-                r.data[k] = h[B * po: B * (po + ld)].reshape(B, ld)[:, :T]
-            elif k == "mel":
-                r.data[k] = h[M * po: M * (po + ld)].reshape(M, ld)[:, :T]
-            elif k == "chroma":
-                r.data[k] = h[12 * po: 12 * (po + ld)].reshape(12, ld)[:, :T]
-            elif k == "tempogram":
-                W = plan.tempogram_win
-                r.data[k] = h[W * po: W * (po + ld)].reshape(W, ld)[:, :T]
-            elif k == "tuning":
-                r.data[k] = float(h[i])
-            elif k in ("onset_env", "autocorr", "flux_linear", "centroid", "rolloff_bin", "frame_max", "hpss_harmonic",
-                       "hpss_percussive"):
-                r.data[k] = h[po: po + T]
-            elif k == "kw_blocks":
-                r.data[k] = h[i, : plan.kw_block_count(ns)]
-            elif k == "rms_momentary":
-                r.data[k] = h[i, : 1 + ns // plan.rms_frames(plan.meter_block)[1]]
-            elif k == "rms_short":
-                r.data[k] = h[i, : 1 + ns // plan.rms_frames(3.0)[1]]
-            elif k in ("lufs", "true_peak"):
-                r.data[k] = float(h[i])
-            else:
-                r.data[k] = h[i]
-        if "ltas" in r.data:
-            r.data["ltas"] = (r.data["ltas"] / T).astype(np.float32)
+            r.data[k] = _cut(plan, batch, i, k, h)
         out.append(r)
     return out
 
 
-def analyse_batch(plan: Plan, tracks: Sequence[np.ndarray], outputs: Iterable[str] = DEFAULT_OUTPUTS) -> list[TrackResult]:
-    """Host arrays in, host results out: H2D copy, fused frontend, D2H copy."""
+def lazy_results(batch: DeviceBatch, bufs: FrontendBuffers) -> list[TrackResult]:
+    """Results whose outputs are copied to the host on first access (the device buffers stay referenced)."""
+    plan = batch.plan
+    host: dict = {}
+
+    def fetch(k):
+        if k not in host:
+            host[k] = bufs.t[k].cpu().numpy()
+        return host[k]
+
+    out = []
+    for i in range(batch.n_tracks):
+        out.append(TrackResult(n_samples=int(batch.n_samples[i]), n_frames=int(batch.n_frames[i]), channels=batch.channels,
+                               loader=(lambda k, i=i: _cut(plan, batch, i, k, fetch(k))), available=tuple(bufs.t)))
+    return out
+
+
+def analyse_batch(plan: Plan, tracks: Sequence[np.ndarray], outputs: Iterable[str] = DEFAULT_OUTPUTS,
+                  lazy: bool = False) -> list[TrackResult]:
+    """Host arrays in, host results out: H2D copy, fused frontend, D2H copy (on first access with ``lazy``)."""
     batch = upload(plan, tracks)
     bufs = FrontendBuffers(batch, outputs)
     run_device(plan, batch, bufs)
-    return download(batch, bufs)
+    return lazy_results(batch, bufs) if lazy else download(batch, bufs)
 
 
 class HostPipeline:

@@ -42,7 +42,11 @@ def time_to_frames(times, sr: int, hop_length: int):
 
 def peak_pick(x: np.ndarray, pre_max: int, post_max: int, pre_avg: int, post_avg: int, delta: float,
               wait: int) -> np.ndarray:
-    """Greedy local-max / above-local-mean picker (librosa 0.10.2 semantics, sequential means in x's dtype)."""
+    """Greedy local-max / above-local-mean picker (librosa 0.10.2 semantics, sequential means in x's dtype).
+
+    The local-maximum test is evaluated for all frames at once (pure comparisons, so exactly the loop's
+    `x[n] == max(window)`); the sequential-mean test and the `wait` rule then run over those candidates only.
+    """
     x = np.asarray(x)
     n_total = x.shape[0]
     pre_max, post_max, pre_avg, post_avg, wait = (int(np.ceil(v)) for v in (pre_max, post_max, pre_avg, post_avg, wait))
@@ -59,21 +63,35 @@ def peak_pick(x: np.ndarray, pre_max: int, post_max: int, pre_avg: int, post_avg
         return np.asarray(peaks, dtype=int)
     first = bool(x[0] >= np.max(x[: min(post_max, n_total)]))
     first = first and bool(x[0] >= seq_mean(0, min(post_avg, n_total)) + acc_t(delta))
-    n = 1
+    n_min = 1
     if first:
         peaks.append(0)
-        n = wait + 1
-    while n < n_total:
-        lo, hi = max(0, n - pre_max), min(n + post_max, n_total)
-        is_peak = bool(x[n] == np.max(x[lo:hi]))
-        if is_peak:
-            lo, hi = max(0, n - pre_avg), min(n + post_avg, n_total)
-            is_peak = bool(x[n] >= seq_mean(lo, hi) + acc_t(delta))
-        if is_peak:
+        n_min = wait + 1
+    # running maximum over [n - pre_max, n + post_max): windows truncated at the ends like the loop's slices
+    pad_lo, pad_hi = pre_max, max(post_max - 1, 0)
+    padded = np.concatenate([np.full(pad_lo, -np.inf, dtype=x.dtype), x, np.full(pad_hi, -np.inf, dtype=x.dtype)])
+    win = np.lib.stride_tricks.sliding_window_view(padded, pad_lo + pad_hi + 1) if padded.size >= pad_lo + pad_hi + 1 else None
+    local_max = win.max(axis=1) if win is not None else np.full(n_total, np.inf, dtype=x.dtype)
+    cand = np.flatnonzero(x == local_max)
+    cand = cand[cand >= 1]
+    if cand.size == 0:
+        return np.asarray(peaks, dtype=int)
+    # sequential means of all candidates at once: the same left-to-right additions in x's dtype, vectorised
+    # over candidates (adding nothing past the end of a truncated window)
+    lo = np.maximum(0, cand - pre_avg)
+    hi = np.minimum(cand + post_avg, n_total)
+    acc = np.zeros(cand.size, dtype=acc_t)
+    for j in range(pre_avg + post_avg):
+        idx = lo + j
+        ok = idx < hi
+        acc = np.where(ok, (acc + x[np.minimum(idx, n_total - 1)].astype(acc_t, copy=False)).astype(acc_t, copy=False), acc)
+    mean = (acc / (hi - lo).astype(acc_t)).astype(acc_t, copy=False)
+    passing = cand[x[cand] >= (mean + acc_t(delta)).astype(acc_t, copy=False)]
+    for n in passing:
+        n = int(n)
+        if n >= n_min:
             peaks.append(n)
-            n += wait + 1
-        else:
-            n += 1
+            n_min = n + wait + 1
     return np.asarray(peaks, dtype=int)
 
 

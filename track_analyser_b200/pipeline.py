@@ -43,6 +43,9 @@ def analyse_track(source, *, output_dir: Optional[str | Path] = None, use_stems:
 
     tick("audio")
     with runtime.frontend_session():
+        if audio.stereo_samples is not None:
+            # mono == mid exactly (utils.py:116), so one fused run on the stereo buffer serves the mono stages too
+            runtime.alias_mono_to_stereo(audio.samples, audio.stereo_samples)
         grid = beat_grid(audio.samples, audio.sample_rate)
         bpm = estimate_bpm(audio.samples, audio.sample_rate)
         beat_result = beats.build_beat_analysis(bpm, grid["time"].to_numpy(), audio.sample_rate, grid=grid)

@@ -50,6 +50,26 @@ def frontend_session():
         _local.cache = prev
 
 
+def alias_mono_to_stereo(mono: np.ndarray, stereo: np.ndarray) -> bool:
+    """Inside a session: let requests for ``mono`` be served by the fused run on ``stereo``.
+
+    Valid when mono is exactly the float32 mean of the two channels (utils.coerce_audio builds it that way,
+    utils.py:116): the stereo kernel's mid spectrum IS the mono spectrum, its K-weighting and true peak run on
+    the same mono mix.  Returns False (and does nothing) when that does not hold."""
+    cache = getattr(_local, "cache", None)
+    mono = np.asarray(mono)
+    stereo = np.asarray(stereo)
+    if cache is None or stereo.ndim != 2 or stereo.shape[0] != 2 or mono.shape != stereo.shape[1:]:
+        return False
+    if mono.dtype != np.float32 or stereo.dtype != np.float32:
+        return False
+    if not np.array_equal(np.mean(stereo, axis=0), mono):
+        return False
+    cache.setdefault("__alias__", {})[_fingerprint(mono)] = _fingerprint(stereo)
+    cache.setdefault("__alias_buf__", {})[_fingerprint(stereo)] = stereo
+    return True
+
+
 def frontend(samples: np.ndarray, sample_rate: int, *, n_fft: int = 2048, hop: int = 512, n_mels: int = 128,
              roll_percent: float = 0.85, meter_block: float = 0.4, outputs=None) -> engine.TrackResult:
     """Run (or fetch) the fused frontend for one track given as (N,), (1, N) or (2, N) float32."""
@@ -60,8 +80,15 @@ def frontend(samples: np.ndarray, sample_rate: int, *, n_fft: int = 2048, hop: i
     want = tuple(outputs) if outputs is not None else None
     key = None
     if cache is not None:
-        key = (_fingerprint(x), int(sample_rate), n_fft, hop, n_mels, float(roll_percent), float(meter_block))
+        fp = _fingerprint(x)
+        src = None
+        if fp in cache.get("__alias__", {}):   # mono view of a stereo buffer that is (or will be) analysed
+            src = cache["__alias__"][fp]
+            fp = src
+        key = (fp, int(sample_rate), n_fft, hop, n_mels, float(roll_percent), float(meter_block))
         hit = cache.get(key)
+        if hit is None and src is not None:
+            x = cache["__alias_buf__"][src]   # run on the stereo buffer; the result also serves the mono requests
         if hit is not None and (want is None or all(o in hit for o in want)):
             return hit
         want = None  # a session computes everything once
@@ -72,7 +99,7 @@ def frontend(samples: np.ndarray, sample_rate: int, *, n_fft: int = 2048, hop: i
     if want is None:  # "everything" means everything this plan can produce
         if n_mels == 0:
             outs = tuple(o for o in outs if o not in ("mel", "onset_env", "autocorr", "flux_linear", "tempogram"))
-    res = engine.analyse_batch(plan, [x], outs)[0]
+    res = engine.analyse_batch(plan, [x], outs, lazy=cache is not None)[0]
     if cache is not None:
         cache[key] = res
     return res
