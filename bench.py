@@ -372,7 +372,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=180.0)
     ap.add_argument("--chunk-tracks", type=int, default=8)
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--ref-seconds", type=float, default=30.0, help="track length of the bounded CPU sample (one track per worker)")
+    ap.add_argument("--ref-seconds", type=float, default=60.0, help="track length of the bounded CPU sample (one track per worker)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

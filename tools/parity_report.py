@@ -92,6 +92,21 @@ def main():
         rows.append(stats("rolloff", freqs[r["rolloff_bin"]], o["rolloff"]))
         rows.append({"name": "rolloff_bins_equal", "pass_rate": float(np.mean(freqs[r["rolloff_bin"]] == o["rolloff"]))})
         rows.append({"name": "lufs", "got": r["lufs"], "ref": o["lufs"], "abs_err": abs(r["lufs"] - o["lufs"])})
+        mono = np.mean(x, axis=0) if x.ndim == 2 else x
+        ref_chroma, ref_tuning = olr.chroma_stft(mono, args.sr, n_fft=args.n_fft, hop_length=args.hop, return_tuning=True)
+        rows.append(stats("chroma", r["chroma"], ref_chroma))
+        rows.append({"name": "tuning", "got": r["tuning"], "ref": ref_tuning, "equal": bool(abs(r["tuning"] - ref_tuning) < 1e-12)})
+        rows.append(stats("tempogram", r["tempogram"], olr.tempogram(onset_envelope=o["onset_env"], sr=args.sr, hop_length=args.hop)))
+        harm, perc = olr.hpss(o["magnitude"])
+        rows.append(stats("hpss_harmonic", r["hpss_harmonic"], np.sum(harm, axis=0, dtype=np.float64)))
+        rows.append(stats("hpss_percussive", r["hpss_percussive"], np.sum(perc, axis=0, dtype=np.float64)))
+        tp_ref = ofe.true_peak_dbtp(mono, args.sr)
+        tp_got = 20.0 * np.log10(r["true_peak"] + 1e-12)
+        rows.append({"name": "true_peak_db", "got": tp_got, "ref": tp_ref, "abs_err": abs(tp_got - tp_ref)})
+        from track_analyser_b200 import hostlogic
+        on_g = hostlogic.onset_detect(r["onset_env"], args.sr, args.hop, backtrack=True)
+        on_o = hostlogic.onset_detect(o["onset_env"], args.sr, args.hop, backtrack=True)
+        rows.append({"name": "onset_frames", "count": int(on_o.size), "bit_exact": bool(np.array_equal(on_g, on_o))})
         rows.append(stats("momentary_db", loudness_host.frames_to_db(r["rms_momentary"]), o["momentary_db"]))
         rows.append(stats("short_db", loudness_host.frames_to_db(r["rms_short"]), o["short_db"]))
         mo = r["moments"]
@@ -106,6 +121,15 @@ def main():
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/parity_report.json", "w") as fh:
         json.dump(report, fh, indent=1)
+    # compact table for profiles/
+    with open("gpurun_out/parity_report.md", "w") as fh:
+        fh.write("| track | output | max abs err | max rel err | |ref| max | pass rate at rtol 1e-4 / atol 1e-6 |\n|---|---|---|---|---|---|\n")
+        for t in report["tracks"]:
+            for row in t["rows"]:
+                if "max_abs" in row:
+                    fh.write(f"| {t['index']} | {row['name']} | {row['max_abs']:.3e} | {row['max_rel']:.3e} | {row['ref_absmax']:.3e} | {row['pass_rate']:.6f} |\n")
+                else:
+                    fh.write(f"| {t['index']} | {row['name']} | " + ", ".join(f"{k}={v}" for k, v in row.items() if k != "name") + " | | | |\n")
 
 
 if __name__ == "__main__":
