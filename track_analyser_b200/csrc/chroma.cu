@@ -59,8 +59,7 @@ __global__ void __launch_bounds__(256) pip_peaks_kernel(const TrackDesc* __restr
         return m * m;
     };
     float sm = S(kmin - 1), s0 = S(kmin);
-    for (int k = kmin; k < kmax; ++k) {
-        const float sp = S(k + 1);
+    auto visit = [&](int k, float sp) {
         const float xm = sm > ref ? sm : 0.f, x0 = s0 > ref ? s0 : 0.f, xp = sp > ref ? sp : 0.f;
         if (x0 > xm && x0 >= xp) {
             // parabolic interpolation (float64 from float32 inputs, result stored as float32)
@@ -79,7 +78,16 @@ __global__ void __launch_bounds__(256) pip_peaks_kernel(const TrackDesc* __restr
         }
         sm = s0;
         s0 = sp;
+    };
+    int k = kmin;
+    for (; k + 8 <= kmax; k += 8) {  // eight row reads in flight per thread: the loop is latency-bound otherwise
+        float nx[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) nx[u] = S(k + 1 + u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) visit(k + u, nx[u]);
     }
+    for (; k < kmax; ++k) visit(k, S(k + 1));
 }
 
 __device__ __forceinline__ unsigned ordered_key(float v) {
