@@ -1,4 +1,4 @@
-// CPU harness for csrc/fft_core.cuh: runs the exact pass code with the group's
+// CPU harness for csrc/fft2_core.cuh: runs the exact pass code with the group's
 // threads emulated by loops and compares against a float64 O(N^2) DFT.
 // Build + run: see tests/test_host_fft_harness.py (nvcc host compile, no GPU needed).
 #include <cmath>
@@ -10,60 +10,6 @@
 #include "../track_analyser_b200/csrc/fft2_core.cuh"
 
 using namespace ta;
-
-template <int N>
-double run() {
-    using C = FftCfg<N>;
-    std::vector<float2> tw1(15 * C::M), tw2(16 * C::Q), ex(C::EX);
-    const double PI = 3.14159265358979323846;
-    for (int k1 = 1; k1 < 16; ++k1)
-        for (int r = 0; r < C::M; ++r) {
-            double a = -2.0 * PI * double((r * k1) % N) / N;
-            tw1[(k1 - 1) * C::M + r] = make_float2((float)cos(a), (float)sin(a));
-        }
-    for (int k2 = 0; k2 < 16; ++k2)
-        for (int n3 = 0; n3 < C::Q; ++n3) {
-            double a = -2.0 * PI * double(n3 * k2) / C::M;
-            tw2[k2 * C::Q + n3] = make_float2((float)cos(a), (float)sin(a));
-        }
-    std::vector<float> a(N), b(N);
-    srand(1234 + N);
-    for (int n = 0; n < N; ++n) {
-        a[n] = (float)rand() / RAND_MAX - 0.5f;
-        b[n] = (float)rand() / RAND_MAX - 0.5f;
-    }
-    std::vector<float2> regs(C::M * 16);
-    auto R = [&](int t) -> float2(&)[16] { return *reinterpret_cast<float2(*)[16]>(&regs[t * 16]); };
-    // pass 1 (inputs pre-scaled by 1/2 as the kernels do)
-    for (int r = 0; r < C::M; ++r) {
-        for (int n1 = 0; n1 < 16; ++n1) R(r)[n1] = make_float2(0.5f * a[n1 * C::M + r], 0.5f * b[n1 * C::M + r]);
-        pass1<N>(R(r), r, tw1.data(), ex.data());
-    }
-    for (int t = 0; t < C::M; ++t) pass2_load<N>(R(t), t, ex.data());
-    for (int t = 0; t < C::M; ++t) pass2_store<N>(R(t), t, tw2.data(), ex.data());
-    for (int t = 0; t < C::M; ++t) pass3_load<N>(R(t), t, ex.data());
-    for (int t = 0; t < C::M; ++t) pass3_store<N>(R(t), t, ex.data());
-    // reference: separate real DFTs of a and b in double
-    double maxerr = 0, maxref = 0;
-    for (int k = 0; k <= N / 2; ++k) {
-        double ar = 0, ai = 0, br = 0, bi = 0;
-        for (int n = 0; n < N; ++n) {
-            double ang = -2.0 * PI * double((long long)n * k % N) / N;
-            double c = cos(ang), s = sin(ang);
-            ar += a[n] * c; ai += a[n] * s; br += b[n] * c; bi += b[n] * s;
-        }
-        float2 xa, xb;
-        split_pair(ex[k], ex[(N - k) & (N - 1)], xa, xb);
-        double e = fabs(xa.x - ar);
-        e = fmax(e, fabs(xa.y - ai));
-        e = fmax(e, fabs(xb.x - br));
-        e = fmax(e, fabs(xb.y - bi));
-        maxerr = fmax(maxerr, e);
-        maxref = fmax(maxref, sqrt(ar * ar + ai * ai));
-    }
-    printf("N=%d maxerr=%.3e maxref=%.3e rel=%.3e\n", N, maxerr, maxref, maxerr / maxref);
-    return maxerr / maxref;
-}
 
 // Packed two-transform core (fft2_core.cuh): transforms A = a + i*b and B = c + i*d share every
 // instruction; barriers of the kernel are the boundaries between the thread loops below.
@@ -225,9 +171,6 @@ double run3() {
 
 int main() {
     double e = 0;
-    e = fmax(e, run<1024>());
-    e = fmax(e, run<2048>());
-    e = fmax(e, run<4096>());
     e = fmax(e, run2<1024>());
     e = fmax(e, run2<2048>());
     e = fmax(e, run2<4096>());

@@ -1,4 +1,4 @@
-"""Runs csrc/fft_core.cuh's pass code on the CPU (threads emulated) against a float64 DFT."""
+"""Runs csrc/fft2_core.cuh's pass code on the CPU (threads emulated) against a float64 DFT."""
 
 import os
 import shutil
