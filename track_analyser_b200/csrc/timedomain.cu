@@ -243,14 +243,26 @@ __global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(
                 }
             }
         };
-        float ln[TD_SEG], rn[TD_SEG];  // software pipeline: the next step's samples are in flight during this step
+        // Software pipeline, two levels deep:
+        //   * the raw samples of the next step are in flight while this step is processed (ln / rn);
+        //   * the two biquad stages are skewed by one step: iteration `it` runs the shelf on step `it` and the
+        //     high-pass on step `it - 1` (y1 = the shelf's rounded output of the previous iteration).  The two
+        //     recurrences + warp scans are independent instruction streams in one basic block, so their DFMA
+        //     dependency chains interleave.  The first iteration feeds the high-pass zeros (state stays zero), the
+        //     last one feeds the shelf zeros.
+        float ln[TD_SEG], rn[TD_SEG];
         load_step(ws, ln, rn);
-        for (long long n0 = ws; n0 < ce; n0 += TD_STEP) {
+        double y1[TD_SEG];
+#pragma unroll
+        for (int i = 0; i < TD_SEG; ++i) y1[i] = 0.0;
+        for (long long n0 = ws; n0 < ce + TD_STEP; n0 += TD_STEP) {
+            const bool have = n0 < ce;                                 // a real step enters stage 1 this iteration
+            const long long nprev = n0 - TD_STEP;                      // the step whose stage 2 runs now
             float l[TD_SEG], r[TD_SEG];
 #pragma unroll
             for (int i = 0; i < TD_SEG; ++i) {
-                l[i] = ln[i];
-                r[i] = rn[i];
+                l[i] = have ? ln[i] : 0.f;
+                r[i] = have ? rn[i] : 0.f;
             }
             if (n0 + TD_STEP < ce) load_step(n0 + TD_STEP, ln, rn);
             const bool warm = n0 < cs0;                              // warm-up step: nothing is accumulated
@@ -266,7 +278,7 @@ __global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(
                     mono[i] = p.stereo ? 0.5f * (l[i] + r[i]) : l[i];
                     x[i] = double(mono[i]);
                 }
-                if (!warm && p.blk_absmax) {
+                if (have && !warm && p.blk_absmax) {
                     float bm = 0.f;
 #pragma unroll
                     for (int i = 0; i < TD_SEG; ++i) bm = fmaxf(bm, fabsf(mono[i]));
@@ -275,7 +287,7 @@ __global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(
                     if (lane == 0) p.blk_absmax[size_t(trk) * p.blk_pitch + size_t(n0 / TD_STEP)] = bm;
                     amax = fmaxf(amax, bm);
                 }
-                if (!warm) {
+                if (have && !warm) {
 #pragma unroll
                     for (int i = 0; i < TD_SEG; ++i) {
                         fMM = fmaf(mono[i], mono[i], fMM);
@@ -322,22 +334,23 @@ __global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(
                     }
                 }
             }
-            // ---- K-weighting: shelf, float32 rounding, high-pass, float32 rounding, squares ----
-            double e0, e1;
-            stage_zero_state(p.stage[0], x, e0, e1, lane);
-            stage_correct(p.stage[0], al[0], x, e0, e1, c10, c11, lane);
-#pragma unroll
-            for (int i = 0; i < TD_SEG; ++i) x[i] = round_f32(x[i]);
-            stage_zero_state(p.stage[1], x, e0, e1, lane);
-            stage_correct(p.stage[1], al[1], x, e0, e1, c20, c21, lane);
-            if (!warm && gk) {
+            // ---- K-weighting: shelf on this step || high-pass on the previous step (straight-line, no branches) ----
+            double ea0, ea1, eb0, eb1;
+            stage_zero_state(p.stage[0], x, ea0, ea1, lane);
+            stage_zero_state(p.stage[1], y1, eb0, eb1, lane);
+            stage_correct(p.stage[0], al[0], x, ea0, ea1, c10, c11, lane);
+            stage_correct(p.stage[1], al[1], y1, eb0, eb1, c20, c21, lane);
+            // y1 now holds the K-weighted samples of the previous step; x the shelf output of this one
+            if (nprev >= cs0 && gk) {
 #pragma unroll
                 for (int i = 0; i < TD_SEG; ++i) {
-                    const double y = round_f32(x[i]);
-                    x[i] = y * y;
+                    const double y = round_f32(y1[i]);
+                    y1[i] = y * y;
                 }
-                granule_add(ga_k, gk, unsigned(p.g_k), inv_k, n32, x, full, td.n_samples, lane);
+                granule_add(ga_k, gk, unsigned(p.g_k), inv_k, unsigned(nprev), y1, nprev + TD_STEP <= td.n_samples, td.n_samples, lane);
             }
+#pragma unroll
+            for (int i = 0; i < TD_SEG; ++i) y1[i] = round_f32(x[i]);  // float32 round trip between the stages
         }
         if (gk) gran_flush(ga_k, gk, lane);
         if (gm) gran_flush(ga_m, gm, lane);
