@@ -258,13 +258,15 @@ __global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(
         for (long long n0 = ws; n0 < ce + TD_STEP; n0 += TD_STEP) {
             const bool have = n0 < ce;                                 // a real step enters stage 1 this iteration
             const long long nprev = n0 - TD_STEP;                      // the step whose stage 2 runs now
+            // in the extra last iteration ln / rn hold whatever follows the chunk (or zeros past the track end): the
+            // shelf output computed from it is never used and nothing of it is accumulated (`have`)
             float l[TD_SEG], r[TD_SEG];
 #pragma unroll
             for (int i = 0; i < TD_SEG; ++i) {
-                l[i] = have ? ln[i] : 0.f;
-                r[i] = have ? rn[i] : 0.f;
+                l[i] = ln[i];
+                r[i] = rn[i];
             }
-            if (n0 + TD_STEP < ce) load_step(n0 + TD_STEP, ln, rn);
+            if (have) load_step(n0 + TD_STEP, ln, rn);
             const bool warm = n0 < cs0;                              // warm-up step: nothing is accumulated
             const bool full = n0 + TD_STEP <= td.n_samples;          // no sample of this step is past the end
             const unsigned n32 = unsigned(n0);
