@@ -10,6 +10,7 @@ planar float32 arrays processed by one launch sequence.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from dataclasses import dataclass, field
 from typing import Iterable, Sequence
 
@@ -142,6 +143,7 @@ class DeviceBatch:
 
 
 _staging: dict = {}
+_staging_lock = threading.Lock()
 
 
 def _pinned_staging(n: int) -> torch.Tensor:
@@ -177,10 +179,11 @@ def upload(plan: Plan, tracks: Sequence[np.ndarray]) -> DeviceBatch:
     if len(chans) != 1 or next(iter(chans)) not in (1, 2):
         raise ValueError("a batch must hold tracks that are all mono (N,) / (1, N) or all stereo (2, N)")
     channels = next(iter(chans))
-    host, offsets, n_samples = pack_host(tracks, channels, reuse=True)
-    dev = torch.empty(host.numel(), dtype=torch.float32, device=f"cuda:{plan.device}")
-    dev.copy_(host, non_blocking=True)
-    torch.cuda.current_stream(dev.device).synchronize()  # the shared staging buffer may be refilled right away
+    with _staging_lock:  # one process-wide pinned staging buffer: fill, copy, and wait before anyone refills it
+        host, offsets, n_samples = pack_host(tracks, channels, reuse=True)
+        dev = torch.empty(host.numel(), dtype=torch.float32, device=f"cuda:{plan.device}")
+        dev.copy_(host, non_blocking=True)
+        torch.cuda.current_stream(dev.device).synchronize()
     return DeviceBatch(plan, dev, offsets, n_samples, channels)
 
 
