@@ -51,6 +51,8 @@ extern "C" {
 #define TA_ERR_UNSUPPORTED (-3)
 #define TA_ERR_WORKSPACE (-4) /* workspace too small */
 
+#define TA_N_MOMENTS 10      /* doubles per track in ta_frontend_out.moments */
+
 typedef struct ta_plan ta_plan;
 
 TA_API int ta_abi_version(void);
@@ -111,7 +113,8 @@ typedef struct ta_frontend_out {
     double* centroid;      /* [P]      spectral centroid, Hz: features.py:97-100 */
     int32_t* rolloff_bin;  /* [P]      roll-off bin index k (frequency = k*sr/n_fft): features.py:116-123 */
     double* band_energy;   /* [n_tracks * 2 * B] per-bin time sums of |mid|^2 then |side|^2: stereo.py:95-122 */
-    double* moments;       /* [n_tracks * 8] sum L, R, L^2, R^2, LR, mid^2, side^2, n: stereo.py:62-83, loudness.py:118 */
+    double* moments;       /* [n_tracks * TA_N_MOMENTS] sum L, R, L^2, R^2, LR, mid^2, side^2, n, sum |L|, sum |R|:
+                              stereo.py:62-83, loudness.py:118, harmony.py:270-282 (mono batches: L = the signal, R = 0) */
     double* kw_blocks;     /* [n_tracks * kw_pitch] K-weighted gating-block mean squares z_j: loudness.py:60-61 */
     double* lufs;          /* [n_tracks] gated integrated loudness: loudness.py:61 */
     double* rms_momentary; /* [n_tracks * rms_pitch] mean-square of centred frames, 0.4 s window: loudness.py:57 */

@@ -68,3 +68,18 @@ def drums_muted_track(sr=22_050, duration=32.0):
         if b > a:
             drums[a:b] += env[: b - a]
     return (harmonic + drums).astype(np.float32), sr, np.arange(0.0, duration, 0.5)
+
+
+def triad_progression(sr=22_050, duration=1.0):
+    """reference tests/test_harmony.py:11-36: C, F, G, C major triads (Hann envelopes), peak-normalised."""
+    def triad(root):
+        t = np.linspace(0.0, duration, int(sr * duration), endpoint=False)
+        chord = np.zeros_like(t)
+        for k in (0, 4, 7):
+            chord += np.sin(2 * np.pi * 440.0 * 2.0 ** ((root + k - 69) / 12.0) * t)  # librosa.midi_to_hz
+        env = np.hanning(t.size)
+        return (chord * env / np.max(env)).astype(np.float32)
+
+    x = np.concatenate([triad(60), triad(65), triad(67), triad(60)])
+    x /= np.max(np.abs(x))
+    return x.astype(np.float32), sr

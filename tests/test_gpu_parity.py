@@ -516,6 +516,35 @@ def test_structure_boundaries_like_reference_test_and_oracle():
         structure.analyse_structure("file.wav", beat, seed=1)
 
 
+# ------------------------------------------------------------------------------ harmony (reference tests/test_harmony.py)
+def test_harmony_like_reference_test():
+    from track_analyser_b200 import harmony
+    from track_analyser_b200.analysis import beats
+    from track_analyser_b200.utils import AudioInput
+
+    x, sr = signals.triad_progression()
+    keys = harmony.key_estimate(x, sr)
+    assert keys.best.key == "C major" and keys.best.confidence > keys.second_best.confidence
+    assert keys.second_best.key in {"G major", "F major"}
+    beat = beats.build_beat_analysis(bpm=60.0, beat_times=np.arange(4) * 1.0, sr=sr)
+    res = harmony.analyse_harmony(AudioInput(samples=x, sample_rate=sr), beat, None, seed=123)
+    assert res.primary_key.key == "C major" and res.primary_key.confidence > res.secondary_key.confidence
+    assert res.secondary_key.key in {"G major", "F major"}
+    times = np.array([p.time for p in res.chord_change_points])
+    assert times.size > 0
+    assert sum(bool(np.any(np.abs(times - b) <= 0.25)) for b in (1.0, 2.0, 3.0)) / 3 >= 0.7
+    assert all(0.0 <= p.strength <= 1.0 for p in res.chord_change_points)
+    # same seed, same suggestions (numpy Generator stream like the reference: harmony.py:143)
+    again = harmony.analyse_harmony(AudioInput(samples=x, sample_rate=sr), beat, None, seed=123)
+    assert res.hook_suggestion.notes.equals(again.hook_suggestion.notes) and res.key_estimate == res.primary_key
+    # the oracle's chroma through the same host logic gives the same integer/label outputs
+    ref_chroma = olr.chroma_stft(x, sr)
+    ref_keys = harmony._rank_keys(*harmony._score_keys([ref_chroma, ref_chroma]))
+    assert ref_keys.best.key == res.primary_key.key and ref_keys.second_best.key == res.secondary_key.key
+    rng = np.random.default_rng(123)
+    assert [h.chord for h in harmony._estimate_chords(ref_chroma, beat, rng)] == [h.chord for h in res.chord_hints]
+
+
 # ------------------------------------------------------------------------------ analyse_track
 def test_analyse_track_pipeline_like_reference():
     from track_analyser_b200 import harmony, pipeline
@@ -547,13 +576,18 @@ def test_analyse_track_pipeline_like_reference():
     lo, mid, hi = ofe.spectral_balance(mono, sr)
     sb = res.harmonic.spectral_balance
     assert (sb.low_band, sb.mid_band, sb.high_band) == pytest.approx((lo, mid, hi), rel=RTOL)
+    hf = harmony.harmony_frontend(audio)
     ref_chroma, ref_tuning = ofe.chroma_stft(mono, sr, return_tuning=True)
-    assert res.harmonic.tuning == pytest.approx(ref_tuning, abs=1e-12)
-    np.testing.assert_allclose(res.harmonic.chroma_stft, ref_chroma, rtol=RTOL, atol=2e-6)
+    assert hf.tuning == pytest.approx(ref_tuning, abs=1e-12)
+    np.testing.assert_allclose(hf.chroma_stft, ref_chroma, rtol=RTOL, atol=2e-6)
     # key index (integer output) from GPU chroma == from oracle chroma
-    k_gpu = harmony.key_index(harmony._rank_keys(*harmony._score_keys([res.harmonic.chroma_stft])))
-    k_ref = harmony.key_index(harmony._rank_keys(*harmony._score_keys([ref_chroma])))
-    assert k_gpu == k_ref
+    k_gpu = harmony.key_index(harmony._rank_keys(*harmony._score_keys([hf.chroma_stft, hf.chroma_stft])))
+    k_ref = harmony.key_index(harmony._rank_keys(*harmony._score_keys([ref_chroma, ref_chroma])))
+    assert k_gpu == k_ref and res.harmonic.primary_key.key == harmony._key_names()[k_ref]
+    assert isinstance(res.harmonic, harmony.HarmonyAnalysis)
+    assert res.harmonic.stereo_image.correlation == pytest.approx(float(np.corrcoef(x[0], x[1])[0, 1]), abs=1e-5)
+    assert res.harmonic.stereo_image.balance == pytest.approx(float(np.mean(np.abs(x[0])) - np.mean(np.abs(x[1]))), abs=1e-6)
+    assert len(res.harmonic.chord_hints) == len(res.beat.beat_frames) and len(res.harmonic.hook_suggestion.notes) == 8
     assert res.loudness.integrated_lufs == pytest.approx(opl.integrated_loudness(mono, sr), abs=0.01)
     assert res.loudness.true_peak_dbfs == pytest.approx(ofe.true_peak_dbtp(mono, sr), abs=1e-4)
     assert res.features.ltas.magnitude.shape == (1025,)

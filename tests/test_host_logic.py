@@ -151,3 +151,28 @@ def test_structure_spacing_helpers():
     assert structure._refine(np.array([3]), np.array([0.0, 0.0, 0.0, 0.1, 0.9, 0.0]), 1).tolist() == [4]
     assert structure._classify([0.1, 0.7, 0.5, 0.2, 0.4, 0.3], [1, 7, 5, 2, 4, 3], [9, 3, 5, 8, 6, 7]) == [
         "intro", "drop", "groove", "breakdown", "bridge", "outro"]
+
+
+def test_harmony_host_logic_on_oracle_chroma():
+    """Key ranking, chord hints, change points and seeded MIDI suggestions (harmony.py:190-465) on the oracle's
+    chroma_stft of the reference's own C-F-G-C test signal (tests/test_harmony.py)."""
+    from track_analyser_b200 import harmony
+    from track_analyser_b200.analysis import beats
+
+    x, sr = signals.triad_progression()
+    chroma = lr.chroma_stft(x, sr)
+    keys = harmony._rank_keys(*harmony._score_keys([chroma, chroma]))
+    assert keys.best.key == "C major" and keys.second_best.key in {"G major", "F major"}
+    assert harmony.key_index(keys) == 0
+    beat = beats.build_beat_analysis(bpm=60.0, beat_times=np.arange(4) * 1.0, sr=sr)
+    hints = harmony._estimate_chords(chroma, beat, np.random.default_rng(123))
+    assert [h.chord[:-3] for h in hints[1:3]] == ["F", "G"] or len(hints) >= 3
+    changes = harmony._detect_chord_changes(chroma, beat, hints)
+    times = np.array([c.time for c in changes])
+    assert sum(bool(np.any(np.abs(times - b) <= 0.25)) for b in (1.0, 2.0, 3.0)) >= 2
+    assert harmony._scale_for_key("A minor") == [9, 11, 0, 2, 4, 5, 7] and harmony._scale_for_key("C major")[:3] == [0, 2, 4]
+    midi = harmony._generate_midi(chroma, beat, keys.best, np.random.default_rng(5), name="bass", octave=-1, start_offset=0.0)
+    assert list(midi.notes.columns) == ["start", "duration", "pitch", "velocity", "channel"] and len(midi.notes) == 4
+    assert midi.notes["pitch"].between(48, 59).all() and midi.notes["velocity"].between(20, 127).all()
+    assert len(harmony._chord_templates()) == 60
+    assert harmony._score_keys([])[0].size == 0 and harmony._rank_keys(np.array([]), []).best.key == "C major"

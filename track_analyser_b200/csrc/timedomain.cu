@@ -57,7 +57,7 @@ struct TdParams {
     double* gran_k;               // [n_tracks][pitch_k]
     double* gran_m;
     double* gran_s;
-    double* moments;              // [n_tracks][8]
+    double* moments;              // [n_tracks][TA_N_MOMENTS]
     const double* lane_pow;       // [2 stages][32 lanes][4]: A^(8*lane)
     float* blk_absmax;            // [n_tracks][blk_pitch] max |mono| of each 256-sample step (nullable)
     uint32_t* absmax_bits;        // [n_tracks] float bits of max |mono|
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(
         const bool vec = ((reinterpret_cast<uintptr_t>(L) & 15) == 0) && (!p.stereo || (reinterpret_cast<uintptr_t>(R) & 15) == 0);
         double c10 = 0, c11 = 0, c20 = 0, c21 = 0;  // carries of stage 1 / stage 2
         GranAcc ga_k, ga_m, ga_s;
-        double sL = 0, sR = 0, sLL = 0, sRR = 0, sLR = 0, sMM = 0, sSS = 0;
+        double sL = 0, sR = 0, sLL = 0, sRR = 0, sLR = 0, sMM = 0, sSS = 0, sAL = 0, sAR = 0;
         float amax = 0.f;  // max |mono| of this chunk (true-peak screening)
 
         // raw samples of the lane's segment at step n0 (zero past the end of the track)
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(
             {
                 // float32 partial sums over the lane's 8 samples (zero padding past the end adds exact zeros)
                 float mono[TD_SEG];
-                float fL = 0.f, fR = 0.f, fLL = 0.f, fRR = 0.f, fLR = 0.f, fMM = 0.f, fSS = 0.f;
+                float fL = 0.f, fR = 0.f, fLL = 0.f, fRR = 0.f, fLR = 0.f, fMM = 0.f, fSS = 0.f, fAL = 0.f, fAR = 0.f;
 #pragma unroll
                 for (int i = 0; i < TD_SEG; ++i) {
                     mono[i] = p.stereo ? 0.5f * (l[i] + r[i]) : l[i];
@@ -295,7 +295,9 @@ __global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(
                         fMM = fmaf(mono[i], mono[i], fMM);
                         fL += l[i];
                         fLL = fmaf(l[i], l[i], fLL);
+                        fAL += fabsf(l[i]);
                         if (p.stereo) {
+                            fAR += fabsf(r[i]);
                             const float sd = 0.5f * (l[i] - r[i]);
                             fR += r[i];
                             fRR = fmaf(r[i], r[i], fRR);
@@ -306,7 +308,9 @@ __global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(
                     sMM += double(fMM);
                     sL += double(fL);
                     sLL += double(fLL);
+                    sAL += double(fAL);
                     if (p.stereo) {
+                        sAR += double(fAR);
                         sR += double(fR);
                         sRR += double(fRR);
                         sLR += double(fLR);
@@ -359,11 +363,12 @@ __global__ void __launch_bounds__(TD_THREADS, TD_MIN_BLOCKS) time_domain_kernel(
         if (gs) gran_flush(ga_s, gs, lane);
         if (p.blk_absmax && lane == 0 && ce > cs0) atomicMax(&p.absmax_bits[trk], __float_as_uint(amax));
         if (p.moments && ce > cs0) {
-            double v[7] = {sL, sR, sLL, sRR, sLR, sMM, sSS};
+            // slot 7 is the sample count (written by the finalize kernel)
+            double v[9] = {sL, sR, sLL, sRR, sLR, sMM, sSS, sAL, sAR};
 #pragma unroll
-            for (int k = 0; k < 7; ++k) {
+            for (int k = 0; k < 9; ++k) {
                 v[k] = warp_sum(v[k]);
-                if (lane == 0) atomicAdd(&p.moments[size_t(trk) * 8 + k], v[k]);
+                if (lane == 0) atomicAdd(&p.moments[size_t(trk) * TA_N_MOMENTS + (k < 7 ? k : k + 1)], v[k]);
             }
         }
     }
@@ -403,7 +408,7 @@ __global__ void __launch_bounds__(256) time_finalize_kernel(const FinParams p) {
     const int trk = blockIdx.x;
     const TrackDesc td = p.tracks[trk];
     const double ns = double(td.n_samples);
-    if (p.moments && threadIdx.x == 0) p.moments[size_t(trk) * 8 + 7] = ns;
+    if (p.moments && threadIdx.x == 0) p.moments[size_t(trk) * TA_N_MOMENTS + 7] = ns;
     // RMS frames: frame j covers hop granules j-1 and j
     for (int s = 0; s < 2; ++s) {
         double* dst = s ? p.rms_s : p.rms_m;
@@ -558,7 +563,7 @@ int run_time_domain(const ta_plan* plan, const HostBatch& hb, const Workspace& w
         TA_CUDA(cudaMemsetAsync(out->true_peak, 0, sizeof(float) * hb.n_tracks, stream));
     }
     TA_CUDA(cudaMemsetAsync(ws.d_granules, 0, sizeof(double) * gran, stream));
-    if (p.moments) TA_CUDA(cudaMemsetAsync(p.moments, 0, sizeof(double) * 8 * hb.n_tracks, stream));
+    if (p.moments) TA_CUDA(cudaMemsetAsync(p.moments, 0, sizeof(double) * TA_N_MOMENTS * hb.n_tracks, stream));
 
     // warm-up length: the slowest K-weighting pole pair is the high-pass double pole of radius r = sqrt(a2);
     // a zero-input response decays like n*r^n, so take the first multiple of 2048 with n*r^n < 1e-10.

@@ -32,6 +32,7 @@ CORE_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o != "tempogram")
 DEFAULT_OUTPUTS = tuple(o for o in CORE_OUTPUTS if o != "magnitude")
 
 
+N_MOMENTS = 10  # TA_N_MOMENTS: sum L, R, L^2, R^2, LR, mid^2, side^2, n, sum |L|, sum |R|
 STAGE_NAMES = ("stft_mel_features", "onset_flux", "autocorrelation", "tempogram", "chroma_stft", "time_domain_loudness")
 
 
@@ -218,7 +219,7 @@ class FrontendBuffers:
             "onset_env": ((P,), torch.float32), "autocorr": ((P,), torch.float64),
             "flux_linear": ((P,), torch.float64), "ltas": ((nt, B), torch.float64),
             "centroid": ((P,), torch.float64), "rolloff_bin": ((P,), torch.int32),
-            "band_energy": ((nt, 2, B), torch.float64), "moments": ((nt, 8), torch.float64),
+            "band_energy": ((nt, 2, B), torch.float64), "moments": ((nt, N_MOMENTS), torch.float64),
             "kw_blocks": ((nt, self.kw_pitch), torch.float64), "lufs": ((nt,), torch.float64),
             "rms_momentary": ((nt, self.rms_pitch), torch.float64), "rms_short": ((nt, self.rms_pitch), torch.float64),
             "frame_max": ((P,), torch.float32), "chroma": ((12 * P,), torch.float32), "tuning": ((nt,), torch.float64),

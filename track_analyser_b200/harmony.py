@@ -1,17 +1,24 @@
 """Harmony analysis (mirror of the reference's ``harmony.py``), frontend half on the GPU.
 
 On the section-8a path: ``_spectral_balance`` (harmony.py:253-267; a 4096/1024 STFT reduced to
-three band ratios) and the ``chroma_stft`` projection (harmony.py:108,149).  ``chroma_cqt``
-(harmony.py:107,148) is a multi-rate constant-Q transform outside that path;
-until it has a kernel, the key/chord logic below runs on the STFT chroma only and says so in
-``HarmonyAnalysis.chroma_source``.  Key scoring, chord hints, change points and MIDI suggestions
-are small host-side decisions on (12, T) chroma, restated from harmony.py:192-465.
+three band ratios) and the ``chroma_stft`` projection (harmony.py:108,149), plus the stereo image
+(harmony.py:270-282) from the time-domain moments.  Key scoring, chord hints, change points and the
+seeded MIDI suggestions are small host-side decisions on (12, T) chroma, restated from
+harmony.py:190-465 so that ``analyse_harmony`` / ``key_estimate`` keep the reference's signatures
+and dataclasses.
+
+KNOWN DEVIATION: the reference feeds ``librosa.feature.chroma_cqt`` (harmony.py:107,148) into the key
+scores, chord hints, change points and MIDI suggestions.  chroma_cqt is a multi-rate constant-Q
+transform whose octave down-sampling goes through libsoxr (librosa's default ``res_type``), which
+cannot be restated or pinned here.  ``_chroma_cqt`` below is
+the single place where that kernel plugs in; until then it returns the STFT chroma, so results are
+reference-shaped but not reference-equal wherever chroma_cqt matters.
 """
 
 from __future__ import annotations
 
 from dataclasses import dataclass, field
-from typing import List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -63,6 +70,28 @@ class ChordChangePoint:
 
 
 @dataclass(slots=True)
+class MidiSuggestion:
+    name: str
+    notes: object  # pandas.DataFrame with columns start, duration, pitch, velocity, channel
+
+
+@dataclass(slots=True)
+class HarmonyAnalysis:
+    spectral_balance: SpectralBalance
+    stereo_image: StereoImage
+    primary_key: KeyEstimate
+    secondary_key: KeyEstimate
+    chord_hints: List[ChordHint]
+    chord_change_points: List[ChordChangePoint]
+    hook_suggestion: MidiSuggestion
+    bass_suggestion: MidiSuggestion
+
+    @property
+    def key_estimate(self) -> KeyEstimate:
+        return self.primary_key
+
+
+@dataclass(slots=True)
 class HarmonyFrontend:
     """GPU outputs of the harmony stage for one track."""
 
@@ -91,13 +120,20 @@ def _spectral_balance(audio: AudioInput) -> SpectralBalance:
 
 
 def _stereo_image(audio: AudioInput) -> StereoImage:
+    """np.corrcoef(L, R) and mean|L| - mean|R| (harmony.py:270-282) from the device's time-domain moments."""
     samples = audio.stereo_samples if audio.stereo_samples is not None else audio.samples
     samples = np.asarray(samples, dtype=np.float32)
     if samples.ndim == 1 or samples.shape[0] < 2:
         return StereoImage(correlation=1.0, balance=0.0)
-    left, right = samples[0], samples[1]
-    corr = float(np.corrcoef(left, right)[0, 1]) if left.size and right.size else 0.0
-    return StereoImage(correlation=corr, balance=float(np.mean(np.abs(left)) - np.mean(np.abs(right))))
+    if samples.shape[1] == 0:
+        return StereoImage(correlation=0.0, balance=0.0)
+    m = runtime.frontend(np.ascontiguousarray(samples[:2]), audio.sample_rate, outputs=("moments",))["moments"]
+    n = float(m[7])
+    cov = m[4] - m[0] * m[1] / n
+    var_l, var_r = m[2] - m[0] * m[0] / n, m[3] - m[1] * m[1] / n
+    denom = np.sqrt(var_l * var_r)
+    corr = float(cov / denom) if denom > 0 else float("nan")  # np.corrcoef of a constant channel is nan as well
+    return StereoImage(correlation=corr, balance=float(m[8] / n - m[9] / n))
 
 
 def _key_names() -> List[str]:
@@ -137,9 +173,9 @@ def _rank_keys(scores: np.ndarray, keys: List[str]) -> KeyEstimation:
 
 
 def key_estimate(y: np.ndarray, sr: int) -> KeyEstimation:
-    """Best and second-best key from the STFT chroma (the reference also adds chroma_cqt scores)."""
-    chroma, _ = chroma_stft(y, sr)
-    return _rank_keys(*_score_keys([chroma]))
+    """Best and second-best key (harmony.py:99-129); the chroma_cqt slot is filled by ``_chroma_cqt``."""
+    with runtime.frontend_session():
+        return _rank_keys(*_score_keys([_chroma_cqt(y, sr), chroma_stft(y, sr)[0]]))
 
 
 def key_index(estimate: KeyEstimation) -> int:
@@ -152,3 +188,129 @@ def harmony_frontend(audio: AudioInput) -> HarmonyFrontend:
         raise TypeError("analyse_harmony expects an AudioInput instance")
     chroma, tuning = chroma_stft(audio.samples, audio.sample_rate)
     return HarmonyFrontend(spectral_balance=_spectral_balance(audio), chroma_stft=chroma, tuning=tuning)
+
+
+def _chroma_cqt(y: np.ndarray, sr: int) -> np.ndarray:
+    """Stand-in for librosa.feature.chroma_cqt (see the module docstring): the STFT chroma."""
+    return chroma_stft(y, sr)[0]
+
+
+def _beat_profiles(chroma: np.ndarray, beat_result: BeatAnalysis):
+    """L2-normalised mean chroma of the 4 frames around each beat (harmony.py:295-304, 354-363)."""
+    out = []
+    for idx, frame in enumerate(beat_result.beat_frames):
+        window = chroma[:, max(0, frame - 2): frame + 2]
+        if window.size == 0:
+            continue
+        mean = np.mean(window, axis=1)
+        nrm = np.linalg.norm(mean)
+        if nrm > 0:
+            out.append((idx, mean / nrm))
+    return out
+
+
+def _chord_templates() -> Dict[str, np.ndarray]:
+    shapes = {"maj": (0, 4, 7), "min": (0, 3, 7), "dim": (0, 3, 6), "sus2": (0, 2, 7), "sus4": (0, 5, 7)}
+    out: Dict[str, np.ndarray] = {}
+    for root, name in enumerate(PITCH_CLASS_NAMES):
+        for quality, steps in shapes.items():
+            t = np.zeros(12)
+            t[[(root + k) % 12 for k in steps]] = 1.0
+            out[f"{name}{quality}"] = t / np.linalg.norm(t)
+    return out
+
+
+def _estimate_chords(chroma: np.ndarray, beat_result: BeatAnalysis, rng: np.random.Generator) -> List[ChordHint]:
+    if not beat_result.beat_frames:
+        return []
+    names, mats = zip(*_chord_templates().items())
+    mats = np.stack(mats)
+    hints = []
+    for idx, profile in _beat_profiles(chroma, beat_result):
+        scores = np.array([float(np.dot(t, profile)) for t in mats])
+        best = int(np.argmax(scores + rng.normal(0.0, 1e-6, size=scores.shape)))  # seeded tie-breaker like the reference
+        hints.append(ChordHint(time=float(beat_result.beat_times[idx]), chord=names[best],
+                               confidence=float(scores[best] / float(np.max(scores + 1e-9)))))
+    return hints
+
+
+def _detect_chord_changes(chroma: np.ndarray, beat_result: BeatAnalysis, chord_hints: Sequence[ChordHint]) -> List[ChordChangePoint]:
+    if len(beat_result.beat_frames) < 2:
+        return []
+    prof = _beat_profiles(chroma, beat_result)
+    if len(prof) < 2:
+        return []
+    times = [float(beat_result.beat_times[i]) for i, _ in prof]
+    strengths = [float(np.clip(1.0 - float(np.clip(np.dot(a[1], b[1]), -1.0, 1.0)), 0.0, 1.0)) for a, b in zip(prof, prof[1:])]
+    arr = np.asarray(strengths)
+    keep = max(1, int(np.ceil(arr.size * 0.9)))
+    threshold = float(np.min(arr)) if keep >= arr.size else float(np.partition(arr, arr.size - keep)[arr.size - keep])
+    threshold = max(threshold, 0.15)
+    found: Dict[float, float] = {}
+    for t, v in zip(times[1:], strengths):
+        if v >= threshold:
+            found[t] = max(found.get(t, 0.0), v)
+    found[times[1]] = max(found.get(times[1], 0.0), strengths[0])
+    if len(chord_hints) >= 2:
+        templates = _chord_templates()
+        for prev, cur in zip(chord_hints, chord_hints[1:]):
+            if cur.chord == prev.chord:
+                continue
+            a, b = templates.get(prev.chord), templates.get(cur.chord)
+            sim = 0.0 if a is None or b is None else float(np.clip(np.dot(a, b), -1.0, 1.0))
+            found[cur.time] = max(found.get(cur.time, 0.0), float(np.clip(1.0 - sim, 0.0, 1.0)))
+    if not found:
+        return []
+    top = max(found.values()) or 1.0
+    return [ChordChangePoint(time=float(t), strength=float(v / top)) for t, v in sorted(found.items())]
+
+
+def _scale_for_key(key: str) -> List[int]:
+    root, _, mode = key.partition(" ")
+    steps = (0, 2, 4, 5, 7, 9, 11) if mode.strip().lower().startswith("major") else (0, 2, 3, 5, 7, 8, 10)
+    return [(PITCH_CLASS_NAMES.index(root) + k) % 12 for k in steps]
+
+
+def _generate_midi(chroma: np.ndarray, beat_result: BeatAnalysis, key: KeyEstimate, rng: np.random.Generator, *, name: str,
+                   octave: int = 0, start_offset: float = 0.0) -> MidiSuggestion:
+    import pandas as pd
+
+    scale = _scale_for_key(key.key)
+    beats_ = [max(0.0, b - start_offset) for b in beat_result.beat_times[:8]] or [0.0, 0.5, 1.0, 1.5]
+    duration = np.median(np.diff(beats_)) if len(beats_) > 1 else 0.5
+    rows = []
+    for t in beats_:  # two draws per note, in the reference's order: scale degree, then velocity offset
+        degree = int(scale[int(rng.integers(0, len(scale)))])
+        velocity = int(np.clip(96 + rng.integers(-12, 12), 20, 127))
+        rows.append({"start": float(t), "duration": float(duration), "pitch": int(60 + degree + octave * 12),
+                     "velocity": velocity, "channel": 0})
+    return MidiSuggestion(name=name, notes=pd.DataFrame(rows, columns=["start", "duration", "pitch", "velocity", "channel"]))
+
+
+def analyse_harmony(audio: AudioInput, beat_result: BeatAnalysis, downbeat_result: Optional[DownbeatAnalysis], *,
+                    seed: int) -> HarmonyAnalysis:
+    """Reference signature (harmony.py:132-139); see the module docstring for the chroma_cqt deviation."""
+    if not isinstance(audio, AudioInput):
+        raise TypeError("analyse_harmony expects an AudioInput instance")
+    seed_everything(seed)
+    rng = deterministic_rng(seed)
+    with runtime.frontend_session():
+        balance = _spectral_balance(audio)
+        image = _stereo_image(audio)
+        cqt_like = _chroma_cqt(audio.samples, audio.sample_rate)
+        stft_chroma = chroma_stft(audio.samples, audio.sample_rate)[0]
+    keys = _rank_keys(*_score_keys([cqt_like, stft_chroma]))
+    hints = _estimate_chords(cqt_like, beat_result, rng)
+    changes = _detect_chord_changes(cqt_like, beat_result, hints)
+    if downbeat_result and downbeat_result.downbeat_times:
+        offset = downbeat_result.downbeat_times[0]
+    else:
+        offset = beat_result.beat_times[0] if beat_result.beat_times else 0.0
+    hook = _generate_midi(cqt_like, beat_result, keys.best, rng, name="hook", start_offset=offset)
+    bass = _generate_midi(cqt_like, beat_result, keys.best, rng, name="bass", octave=-1, start_offset=offset)
+    return HarmonyAnalysis(spectral_balance=balance, stereo_image=image, primary_key=keys.best, secondary_key=keys.second_best,
+                           chord_hints=hints, chord_change_points=changes, hook_suggestion=hook, bass_suggestion=bass)
+
+
+__all__ = ["HarmonyAnalysis", "ChordChangePoint", "ChordHint", "KeyEstimation", "KeyEstimate", "MidiSuggestion",
+           "SpectralBalance", "StereoImage", "analyse_harmony", "key_estimate"]

@@ -4,8 +4,8 @@
 ``analyse_track`` its signature and stage order (pipeline.py:32-120).  One ``frontend_session``
 spans the call, so the >= 11 identical STFT requests of the reference become one
 fused GPU run per distinct (buffer, n_fft, hop).  ``structure`` is the reference's ``StructureAnalysis`` (HPSS curves from csrc/hpss.cu, host logic
-restated in analysis/structure.py); ``harmonic`` holds the GPU frontend outputs of the harmony stage
-(``HarmonyFrontend``): the chroma_cqt-based key/chord logic behind it is outside section 8a.
+restated in analysis/structure.py); ``harmonic`` is the reference's ``HarmonyAnalysis`` with the STFT chroma standing in for
+chroma_cqt (see harmony.py's docstring: the constant-Q transform is the one section-8f row not on the device).
 """
 
 from __future__ import annotations
@@ -55,7 +55,7 @@ def analyse_track(source, *, output_dir: Optional[str | Path] = None, use_stems:
         tick("structure")
         loudness_result = loudness.analyse_loudness(audio, seed=seed)
         tick("loudness")
-        harmonic_result = harmony.harmony_frontend(audio)
+        harmonic_result = harmony.analyse_harmony(audio, beat_result, downbeat_result, seed=seed)
         tick("harmonic")
         feature_result = features.analyse_features(audio)
         tick("features")
