@@ -281,12 +281,17 @@ def ours(args, rank, world, local_rank):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            stage += np.asarray(engine.run_device_profiled(plan, batch, bufs))
+            engine.run_device(plan, batch, bufs)   # the production call: time-domain pass overlapped on a second stream
         e1.record()
         barrier()
         ms_kernel = e0.elapsed_time(e1) / args.steps
-    launches = engine.launch_count() - launches0
-    stage /= args.steps
+        launches = engine.launch_count() - launches0
+        # per-stage device times (sequential, event-bracketed inside the library) for the roofline figure
+        prof_steps = max(1, min(args.steps, 5))
+        for _ in range(prof_steps):
+            stage += np.asarray(engine.run_device_profiled(plan, batch, bufs))
+        barrier()
+    stage /= prof_steps
     t = torch.tensor([ms_kernel], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -344,6 +349,7 @@ def ours(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world),
             "stage_ms": {k: float(v) for k, v in zip(engine.STAGE_NAMES, stage)},
+            "stage_ms_note": "stages timed one after another; ms_per_step runs the time-domain pass on a second stream",
             "roofline": {"bound": "hbm", "kernel": "stft_fused_kernel<2048,16,stereo,4>", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",

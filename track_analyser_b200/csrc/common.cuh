@@ -67,6 +67,9 @@ struct ta_plan {
     float tp_coef[8 * 21];
     float tp_gain;   // max over branches of sum |c|: |y| <= tp_gain * max |x| over the 21-sample window
     float tp_floor;  // |y[8q]| >= tp_floor * |x[q]| at the sample of largest magnitude
+    // second stream for the time-domain pass of the fused run (it only reads the PCM, so it forks at the
+    // start of ta_frontend_run and joins at its end; see plan.cu frontend_impl)
+    cudaStream_t aux_stream = nullptr;
     // host copies
     std::vector<float> h_window;
     std::vector<float> h_mel_dense;

@@ -1,6 +1,7 @@
 // Plan construction (host-side tables computed in double), error plumbing, batch
 // descriptors, workspace carve-up and the fused schedule of the C ABI.
 #include <atomic>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -375,6 +376,10 @@ int ta_plan_create(const ta_plan_desc* desc, ta_plan** out) {
     TA_REQUIRE(p, "out of host memory");
     p->desc = *desc;
     int rc = plan_build(p);
+    if (rc == TA_OK && cudaStreamCreateWithFlags(&p->aux_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        set_error("cudaStreamCreateWithFlags failed");
+        rc = TA_ERR_CUDA;
+    }
     if (rc != TA_OK) {
         ta_plan_destroy(p);
         return rc;
@@ -392,6 +397,7 @@ void ta_plan_destroy(ta_plan* p) {
     cudaFree(p->d_mel_start);
     cudaFree(p->d_mel_len);
     cudaFree(p->d_mel_woff);
+    if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
     cudaFree(p->d_mel_w);
     cudaFree(p->d_tg_tw1);
     cudaFree(p->d_tg_tw2);
@@ -542,40 +548,82 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
     if (rc != TA_OK) return rc;
     auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], st); };
     mark(0);
+    // The time-domain pass (K5/K6/K8) depends on nothing but the PCM.  Outside the profiled run it is forked onto the
+    // plan's second stream right here, so that its FP64-bound CTAs fill whatever the FFT-bound and HBM-bound kernels of the
+    // main chain leave idle, and joined before returning (the caller's stream sees all results in order).
+    const bool need_td = out->moments || out->kw_blocks || out->lufs || out->rms_momentary || out->rms_short || out->true_peak;
+    static const bool overlap_enabled = [] { const char* e = std::getenv("TA_OVERLAP"); return !(e && e[0] == '0'); }();
+    const bool fork_td = need_td && !ev && overlap_enabled && plan->aux_stream;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    if (fork_td) {
+        TA_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        TA_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        TA_CUDA(cudaEventRecord(ev_fork, st));
+        TA_CUDA(cudaStreamWaitEvent(plan->aux_stream, ev_fork, 0));
+        rc = run_time_domain(plan, hb, ws, out, plan->aux_stream);
+        cudaEventRecord(ev_join, plan->aux_stream);
+        if (rc != TA_OK) {
+            cudaStreamWaitEvent(st, ev_join, 0);
+            cudaEventDestroy(ev_fork);
+            cudaEventDestroy(ev_join);
+            return rc;
+        }
+    }
+    auto join = [&]() {
+        if (fork_td) {
+            cudaStreamWaitEvent(st, ev_join, 0);
+            cudaEventDestroy(ev_fork);  // destruction is deferred by the runtime until the events have completed
+            cudaEventDestroy(ev_join);
+        }
+    };
     const bool need_flux = out->onset_env || out->flux_linear || out->autocorr || out->tempogram;
-    TA_REQUIRE(!need_flux || out->mel, "onset/autocorr outputs need the mel output buffer");
-    TA_REQUIRE(!out->autocorr || out->onset_env, "autocorr output needs the onset_env output buffer");
-    TA_REQUIRE(!out->chroma || (out->magnitude && out->frame_max && out->tuning),
-               "chroma output needs the magnitude, frame_max and tuning buffers");
-    TA_REQUIRE(!out->tempogram || out->onset_env, "tempogram output needs the onset_env buffer");
+    if (need_flux && !out->mel) { join(); set_error("onset/autocorr outputs need the mel output buffer"); return TA_ERR_INVALID; }
+    if (out->autocorr && !out->onset_env) { join(); set_error("autocorr output needs the onset_env output buffer"); return TA_ERR_INVALID; }
+    if (out->chroma && !(out->magnitude && out->frame_max && out->tuning)) {
+        join();
+        set_error("chroma output needs the magnitude, frame_max and tuning buffers");
+        return TA_ERR_INVALID;
+    }
+    if (out->tempogram && !out->onset_env) { join(); set_error("tempogram output needs the onset_env buffer"); return TA_ERR_INVALID; }
     const bool need_stft = out->magnitude || out->mel || out->ltas || out->centroid || out->rolloff_bin || out->band_energy ||
                            out->frame_max;
-    if (need_stft && (rc = run_stft_features(plan, hb, ws, out, st)) != TA_OK) return rc;
+    if (need_stft && (rc = run_stft_features(plan, hb, ws, out, st)) != TA_OK) { join(); return rc; }
     mark(1);
     if (need_flux && (rc = run_onset_flux(plan, hb, ws.d_tracks, out->mel, ws.d_mel_max, out->onset_env,
-                                          out->flux_linear, st)) != TA_OK)
+                                          out->flux_linear, st)) != TA_OK) {
+        join();
         return rc;
+    }
     mark(2);
     if (out->autocorr &&
-        (rc = run_autocorrelate(plan, hb, ws.d_tracks, out->onset_env, out->autocorr, ws.d_fft, ws.fft_elems, st)) != TA_OK)
+        (rc = run_autocorrelate(plan, hb, ws.d_tracks, out->onset_env, out->autocorr, ws.d_fft, ws.fft_elems, st)) != TA_OK) {
+        join();
         return rc;
+    }
     mark(3);
-    if (out->tempogram && (rc = run_tempogram(plan, hb, ws.d_tracks, out->onset_env, out->tempogram, st)) != TA_OK) return rc;
+    if (out->tempogram && (rc = run_tempogram(plan, hb, ws.d_tracks, out->onset_env, out->tempogram, st)) != TA_OK) { join(); return rc; }
     mark(4);
     if (out->chroma && (rc = run_chroma(plan, hb, ws.d_tracks, out->magnitude, out->frame_max, out->chroma, out->tuning,
-                                        ws.d_chroma, ws.chroma_bytes, st)) != TA_OK)
+                                        ws.d_chroma, ws.chroma_bytes, st)) != TA_OK) {
+        join();
         return rc;
+    }
     if (out->hpss_harmonic || out->hpss_percussive) {
-        TA_REQUIRE(out->magnitude && out->hpss_scratch && out->hpss_harmonic && out->hpss_percussive,
-                   "hpss outputs need the magnitude buffer, hpss_scratch and both sum buffers");
+        if (!(out->magnitude && out->hpss_scratch && out->hpss_harmonic && out->hpss_percussive)) {
+            join();
+            set_error("hpss outputs need the magnitude buffer, hpss_scratch and both sum buffers");
+            return TA_ERR_INVALID;
+        }
         if ((rc = run_hpss(plan, hb, ws.d_tracks, out->magnitude, out->hpss_scratch, out->hpss_harmonic, out->hpss_percussive,
-                           st)) != TA_OK)
+                           st)) != TA_OK) {
+            join();
             return rc;
+        }
     }
     mark(5);
-    const bool need_td = out->moments || out->kw_blocks || out->lufs || out->rms_momentary || out->rms_short || out->true_peak;
-    if (need_td && (rc = run_time_domain(plan, hb, ws, out, st)) != TA_OK) return rc;
+    if (need_td && !fork_td && (rc = run_time_domain(plan, hb, ws, out, st)) != TA_OK) return rc;
     mark(6);
+    join();
     return TA_OK;
 }
 
