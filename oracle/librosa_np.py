@@ -406,13 +406,31 @@ def softmask(X, X_ref, power=2.0):
     return mask
 
 
-def hpss(S, kernel_size=31, power=2.0, margin=1.0):
+def _median_filter_reflect(S, kernel_size, axis):
+    """scipy.ndimage.median_filter(S, size=kernel_size along `axis`, mode="reflect").
+
+    The scipy in this image (1.18.1) returns a wrong median for lines of exactly two samples when the first is the
+    larger one (its 1-D fast path; lengths 1, 3 ... 40 agree with the definition, checked against explicit symmetric
+    padding).  The reference pins scipy 1.11.4, which has no such path, so that one length is evaluated from the
+    definition: np.pad(mode="symmetric") is scipy's "reflect".
+    """
     import scipy.ndimage
 
+    if S.shape[axis] != 2:
+        size = [1] * S.ndim
+        size[axis] = kernel_size
+        return scipy.ndimage.median_filter(S, size=tuple(size), mode="reflect")
+    pad = [(0, 0)] * S.ndim
+    pad[axis] = (kernel_size // 2, kernel_size // 2)
+    win = np.lib.stride_tricks.sliding_window_view(np.pad(S, pad, mode="symmetric"), kernel_size, axis=axis)
+    return np.median(win, axis=-1).astype(S.dtype)
+
+
+def hpss(S, kernel_size=31, power=2.0, margin=1.0):
     harm = np.empty_like(S)
-    harm[:] = scipy.ndimage.median_filter(S, size=(1, kernel_size), mode="reflect")
+    harm[:] = _median_filter_reflect(S, kernel_size, axis=1)
     perc = np.empty_like(S)
-    perc[:] = scipy.ndimage.median_filter(S, size=(kernel_size, 1), mode="reflect")
+    perc[:] = _median_filter_reflect(S, kernel_size, axis=0)
     mask_harm = softmask(harm, perc * margin, power=power)
     mask_perc = softmask(perc, harm * margin, power=power)
     return S * mask_harm, S * mask_perc

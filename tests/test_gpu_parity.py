@@ -245,6 +245,29 @@ def test_edge_inputs(name):
         assert abs(r["lufs"] - opl.integrated_loudness(x, sr)) < 0.01
 
 
+@pytest.mark.parametrize("n_fft,hop,mels", [(2048, 512, 128), (1024, 256, 64), (4096, 256, 256)])
+@pytest.mark.parametrize("channels", [1, 2])
+def test_ragged_edge_batches_every_kernel(n_fft, hop, mels, channels):
+    """Every output on a ragged batch that contains a track shorter than one FFT frame (odd length): no fault, finite
+    results, and the short track's spectrum equals the oracle's."""
+    sr = 44_100
+    tracks = [synth.synth_track(3 + i, d, sr, channels) for i, d in enumerate((0.51, 1.237, 0.9))]
+    tracks.append(tracks[0][..., :1001])
+    outs = tuple(o for o in engine.ALL_OUTPUTS if o not in ("kw_blocks", "lufs"))
+    res = engine.analyse_batch(plan_for(sr, n_fft, hop, mels), tracks, outs)
+    for r, x in zip(res, tracks):
+        for k in ("mel", "onset_env", "chroma", "tempogram", "hpss_harmonic", "rms_momentary"):
+            assert np.all(np.isfinite(r[k])), k
+        assert r.n_frames == 1 + x.shape[-1] // hop
+    mono = np.mean(tracks[-1], axis=0) if channels == 2 else tracks[-1]
+    mag = np.abs(olr.stft(mono, n_fft=n_fft, hop_length=hop))
+    frame_norm = np.sqrt(np.sum(mag.astype(np.float64) ** 2, axis=0, keepdims=True) * 2 / n_fft)
+    assert np.all(np.abs(res[-1]["magnitude"] - mag) <= 1e-6 + 1e-4 * mag + 1.5e-6 * frame_norm)
+    harm, perc = olr.hpss(mag)
+    scale = float(np.max(np.sum(harm + perc, axis=0))) + 1e-12
+    np.testing.assert_allclose(res[-1]["hpss_percussive"], np.sum(perc, axis=0), rtol=RTOL, atol=1e-5 * scale)
+
+
 def test_channel_layouts_agree():
     sr = 44_100
     mono = synth.synth_track(3, 2.0, sr, 1)
