@@ -343,6 +343,16 @@ def ours(args, rank, world, local_rank):
                 traffic = tj["traffic_bytes"]
         except Exception:
             pass
+        # algorithmic bytes of the other stages, per launch of this batch
+        stage_bytes = {
+            "stft_mel_features": k1_bytes,
+            "onset_flux": nt * (4 * N_MELS * T + 12 * T),
+            "autocorrelation": nt * (4 * T + 8 * T),
+            "tempogram": nt * (4 * T + 4 * 384 * T),
+            "chroma_stft": nt * (4 * B * T + 48 * T),
+            "time_domain_loudness": nt * (4 * 2 * n),
+        }
+        stage_gbs = {k: stage_bytes[k] / (max(v, 1e-9) * 1e-3) / 1e9 for k, v in zip(engine.STAGE_NAMES, stage)}
         line = {
             "metric": METRIC, "value": world * audio_per_step / (ms_kernel_max * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_kernel_max, "higher_is_better": True,
@@ -350,6 +360,7 @@ def ours(args, rank, world, local_rank):
             "config": workload_config(args, world),
             "stage_ms": {k: float(v) for k, v in zip(engine.STAGE_NAMES, stage)},
             "stage_ms_note": "stages timed one after another; ms_per_step runs the time-domain pass on a second stream",
+            "stage_hbm_frac": {k: float(v / peak) for k, v in stage_gbs.items()},
             "roofline": {"bound": "hbm", "kernel": "stft_fused_kernel<2048,16,stereo,4>", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
