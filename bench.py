@@ -223,8 +223,38 @@ def workload_config(args, world):
     }
 
 
+def bind_to_gpu_numa(index: int):
+    """Pin this process to the CPUs local to GPU `index` (its PCIe root's NUMA node) before any pinned host buffer is
+    allocated, so that every rank's staging memory sits next to its own GPU.  Best effort: returns a note for the
+    JSON line."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        bus = nv.nvmlDeviceGetPciInfo(nv.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{int(dom, 16):04x}:{rest.lower()}"
+        cpus = set()
+        for part in open(path + "/local_cpulist").read().strip().split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        node = open(path + "/numa_node").read().strip()
+        if cpus and cpus != allowed:
+            os.sched_setaffinity(0, cpus)
+            return f"numa node {node}, {len(cpus)} cpus"
+        return f"numa node {node}, affinity unchanged"
+    except Exception as exc:  # no sysfs entry, no NVML, restricted container ...
+        return f"unbound ({type(exc).__name__})"
+
+
 # ----------------------------------------------------------------------------- our arm
 def ours(args, rank, world, local_rank):
+    numa_note = bind_to_gpu_numa(local_rank) if world > 1 else "single rank"
     workers = cpu_workers(world)
     # 1. host pool of distinct synthetic tracks (and, on rank 0 at N=1, the CPU baseline) BEFORE CUDA init: fork-safe
     pool_n = min(args.pool, args.tracks_per_gpu)
@@ -370,6 +400,7 @@ def ours(args, rank, world, local_rank):
                     "steps": e2e_steps, "s_per_step": s_e2e_max, "chunk_tracks": chunk},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
+            "host_binding": numa_note,
         }
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
