@@ -422,6 +422,18 @@ def test_tempogram_matches_oracle(sr, seconds):
     np.testing.assert_allclose(r["tempogram"][0], np.where(np.abs(ref[0]) > 0, 1.0, 0.0), atol=1e-6)  # lag 0 is the max
 
 
+def test_tempogram_other_window_length():
+    """Window lengths other than librosa's default 384 take the unpruned instantiation of the kernel."""
+    sr = 44_100
+    x = synth.synth_track(33, 5.0, sr, 1)
+    plan = engine.Plan(sr, 2048, 512, 128, device=0, tempogram_win=200)
+    r = engine.analyse_batch(plan, [x], ("onset_env", "tempogram"))[0]
+    env = olr.onset_strength(y=x, sr=sr, hop_length=512)
+    ref = olr.tempogram(onset_envelope=env, sr=sr, hop_length=512, win_length=200)
+    assert r["tempogram"].shape == ref.shape == (200, r.n_frames)
+    np.testing.assert_allclose(r["tempogram"], ref, rtol=RTOL, atol=5e-6)
+
+
 def test_tempogram_short_track_inside_window():
     sr = 44_100
     g = np.load(os.path.join(GOLDEN, "tiny_click.npz"))  # T = 175 < 384

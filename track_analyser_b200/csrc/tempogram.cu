@@ -48,6 +48,10 @@ __device__ __forceinline__ float padded_env(const float* __restrict__ x, int T, 
     return x[i];
 }
 
+// WIN > 0: the window length is a compile-time constant, so the transform is pruned by the compiler: pass 1 of the
+// first transform sees the rows n1 >= WIN/64 as literal zeros and pass 3 of the second one only computes the lags
+// below WIN.  WIN == 0: window length from the parameters (any even length <= 512).
+template <int WIN>
 __global__ void __launch_bounds__(512, 1) tempogram_kernel(const TgParams p) {
     using namespace p2;
     using C = FftCfg<TG_N>;
@@ -56,12 +60,13 @@ __global__ void __launch_bounds__(512, 1) tempogram_kernel(const TgParams p) {
     static_assert(NG * 4 == TG_TF, "one round of slots (4 frames each) fills a tile");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* tile = reinterpret_cast<float*>(smem_raw);  // [win][TFP]
-    const size_t tile_bytes = ((size_t(p.win) * TFP * 4 + 15) / 16) * 16;
+    const size_t tile_bytes = ((size_t(WIN > 0 ? WIN : p.win) * TFP * 4 + 15) / 16) * 16;
     float4* ex_all = reinterpret_cast<float4*>(smem_raw + tile_bytes);
     float2* tw1s = reinterpret_cast<float2*>(ex_all + size_t(NG) * E::SLOTS);
     float2* tw2s = tw1s + 15 * M;
     float* red = reinterpret_cast<float*>(tw2s + 16 * C::Q);  // [16 warps][4]
 
+    const int win = WIN > 0 ? WIN : p.win;
     const int tid = threadIdx.x, g = tid / M, r = tid % M, lane = tid & 31, warp = tid >> 5;
     float4* ex = ex_all + size_t(g) * E::SLOTS;
     for (int i = tid; i < 15 * M; i += 512) tw1s[i] = p.tw1[i];
@@ -70,10 +75,10 @@ __global__ void __launch_bounds__(512, 1) tempogram_kernel(const TgParams p) {
 #pragma unroll
     for (int n1 = 0; n1 < 16; ++n1) {
         const int n = n1 * M + r;
-        wreg[n1] = (n < p.win) ? 0.5f * p.window[n] : 0.f;  // 1/2: Hermitian split scaling
+        wreg[n1] = (n < win) ? 0.5f * p.window[n] : 0.f;  // 1/2: Hermitian split scaling
     }
     __syncthreads();
-    const int half = p.win / 2;
+    const int half = win / 2;
 
     for (int w = blockIdx.x; w < p.total_tiles; w += gridDim.x) {
         int lo = 0, hi = p.n_tracks - 1;
@@ -92,7 +97,7 @@ __global__ void __launch_bounds__(512, 1) tempogram_kernel(const TgParams p) {
 #pragma unroll
             for (int n1 = 0; n1 < 16; ++n1) {
                 const int n = n1 * M + r;
-                if (n < p.win) {
+                if ((WIN > 0 && WIN % M == 0) ? (n1 < WIN / M) : (n < win)) {
                     const float a0 = padded_env(x, T, half, t + n), a1 = padded_env(x, T, half, t + 1 + n);
                     const float a2 = padded_env(x, T, half, t + 2 + n), a3 = padded_env(x, T, half, t + 3 + n);
                     v[n1].re = pmuls(make_float2(a0, a1), wreg[n1]);
@@ -136,7 +141,7 @@ __global__ void __launch_bounds__(512, 1) tempogram_kernel(const TgParams p) {
 #pragma unroll
                 for (int k3 = 0; k3 < C::Q; ++k3) {
                     const int lag = r + M * (b + 4 * k3);
-                    if (lag < p.win) {
+                    if ((WIN > 0 && WIN % M == 0) ? (b + 4 * k3 < WIN / M) : (lag < win)) {
                         const C2 z = u[b * C::Q + k3];
                         m0 = fmaxf(m0, fabsf(z.re.x));
                         m1 = fmaxf(m1, fabsf(z.re.y));
@@ -165,7 +170,7 @@ __global__ void __launch_bounds__(512, 1) tempogram_kernel(const TgParams p) {
 #pragma unroll
                 for (int k3 = 0; k3 < C::Q; ++k3) {
                     const int lag = r + M * (b + 4 * k3);
-                    if (lag < p.win) {
+                    if ((WIN > 0 && WIN % M == 0) ? (b + 4 * k3 < WIN / M) : (lag < win)) {
                         const C2 z = u[b * C::Q + k3];
                         *reinterpret_cast<float2*>(tile + lag * TFP + f) = make_float2(z.re.x * s0, z.re.y * s1);
                         *reinterpret_cast<float2*>(tile + lag * TFP + f + 2) = make_float2(z.im.x * s2, z.im.y * s3);
@@ -176,9 +181,9 @@ __global__ void __launch_bounds__(512, 1) tempogram_kernel(const TgParams p) {
         {   // rows of 32 frames -> global, 64-bit accesses, 4 rows per warp instruction? no: 16 lanes per row
             const int hw = tid >> 4, fp = tid & 15;
             const bool ok0 = 2 * fp < nf, ok1 = 2 * fp + 1 < nf;
-            float* dst = p.out + size_t(td.pitch_off) * p.win + t0 + 2 * fp;
+            float* dst = p.out + size_t(td.pitch_off) * win + t0 + 2 * fp;
             if (ok0)
-                for (int lag = hw; lag < p.win; lag += 32) {
+                for (int lag = hw; lag < win; lag += 32) {
                     const float2 a = *reinterpret_cast<const float2*>(tile + lag * TFP + 2 * fp);
                     if (ok1) *reinterpret_cast<float2*>(dst + size_t(lag) * td.ld) = a;
                     else dst[size_t(lag) * td.ld] = a.x;
@@ -206,9 +211,14 @@ int run_tempogram(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_t
     p.out = out;
     const size_t smem = ((size_t(win) * TG_TFP * 4 + 15) / 16) * 16 + size_t(8) * p2::Ex<TG_N>::SLOTS * 16 + size_t(15) * C::M * 8 +
                         size_t(16) * C::Q * 8 + 16 * 4 * 4;
-    TA_CUDA(cudaFuncSetAttribute(tempogram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int grid = std::max(1, std::min(plan->sm_count, p.total_tiles));
-    tempogram_kernel<<<grid, 512, smem, stream>>>(p);
+    if (win == 384) {  // librosa's default: pruned instantiation
+        TA_CUDA(cudaFuncSetAttribute(tempogram_kernel<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tempogram_kernel<384><<<grid, 512, smem, stream>>>(p);
+    } else {
+        TA_CUDA(cudaFuncSetAttribute(tempogram_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tempogram_kernel<0><<<grid, 512, smem, stream>>>(p);
+    }
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TA_OK;
