@@ -340,6 +340,7 @@ def ours(args, rank, world, local_rank):
     def consume(ci, first, cnt, host_out):
         sink.append(float(host_out["lufs"][:cnt].sum()))  # host reads the step's result
 
+    d2h_chunk_full = pipe.d2h_bytes_per_chunk
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
     for _ in range(min(args.warmup, 1) or 1):
         pipe.run(tracks, consume)
@@ -354,6 +355,31 @@ def ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     s_e2e_max = float(t.item())
     n_chunks = (nt + chunk - 1) // chunk
+
+    # ---- informational: the byte-reduced pipeline that analyse_track's host stages need -----------------------------
+    # (HPSS curves and true peak computed on the device, magnitude and tempogram never downloaded; NOT the contract's
+    # e2e figure, which copies every frontend output back)
+    e2e_analysis = None
+    if not args.no_analysis_leg:
+        del pipe
+        torch.cuda.empty_cache()
+        pipe_a = engine.HostPipeline(plan, n, 2, chunk, engine.ANALYSIS_OUTPUTS)
+        pipe_a.run(tracks, consume)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            pipe_a.run(tracks, consume)
+        barrier()
+        ta = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        e2e_analysis = {"value": world * audio_per_step / float(ta.item()), "unit": UNIT, "s_per_step": float(ta.item()),
+                        "h2d_bytes_per_step": nt * 2 * n * 4, "d2h_bytes_per_step": n_chunks * pipe_a.d2h_bytes_per_chunk,
+                        "note": "outputs consumed by analyse_track's host stages (HPSS curves + true peak on the device; "
+                                "magnitude and tempogram stay in HBM)"}
+        d2h_full = n_chunks * d2h_chunk_full
+    else:
+        d2h_full = n_chunks * d2h_chunk_full
 
     if rank == 0:
         B = N_FFT // 2 + 1
@@ -396,12 +422,14 @@ def ours(args, rank, world, local_rank):
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "algorithmic_bytes_per_launch": k1_bytes},
             "e2e": {"value": world * audio_per_step / s_e2e_max, "unit": UNIT,
-                    "h2d_bytes_per_step": nt * 2 * n * 4, "d2h_bytes_per_step": n_chunks * pipe.d2h_bytes_per_chunk,
+                    "h2d_bytes_per_step": nt * 2 * n * 4, "d2h_bytes_per_step": d2h_full,
                     "steps": e2e_steps, "s_per_step": s_e2e_max, "chunk_tracks": chunk},
             "gpu_launches": int(launches),
             "clocks": clk.summary(),
             "host_binding": numa_note,
         }
+        if e2e_analysis:
+            line["e2e_analysis_outputs"] = e2e_analysis
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
@@ -422,6 +450,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--ref-seconds", type=float, default=60.0, help="track length of the bounded CPU sample (one track per worker)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-analysis-leg", action="store_true", help="skip the informational byte-reduced end-to-end leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -27,6 +27,9 @@ ALL_OUTPUTS = (
 # SURVEY section 8a (the north-star frontend): what bench.py measures.  true_peak and the HPSS curves are
 # section-8f "next" rows.
 FRONTEND_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o not in ("true_peak", "hpss_harmonic", "hpss_percussive"))
+# What the host-side stages of pipeline.analyse_track consume: neither the magnitude (HPSS runs on the device) nor the
+# plot-only tempogram leave the GPU.
+ANALYSIS_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o not in ("magnitude", "tempogram"))
 # the bench / default frontend: everything the per-track analysis consumes except the plot-only tempogram
 CORE_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o != "tempogram")
 DEFAULT_OUTPUTS = tuple(o for o in CORE_OUTPUTS if o != "magnitude")
@@ -361,15 +364,18 @@ class HostPipeline:
         ns = np.full(self.chunk, self.n_samples, dtype=np.int64)
         self.dev_in = [torch.empty(self.chunk * self.stride, dtype=torch.float32, device=dev) for _ in range(2)]
         self.batches = [DeviceBatch(plan, d, offsets, ns, channels) for d in self.dev_in]
+        self.requested = tuple(outputs)
         self.bufs = [FrontendBuffers(b, outputs) for b in self.batches]
-        self.host_out = [{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in bf.t.items()}
-                         for bf in self.bufs]
+        # only what was asked for is copied back; buffers that exist because another output needs them (the magnitude
+        # for chroma / HPSS, the mel for the onset envelope ...) stay on the device
+        self.host_out = [{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in bf.t.items()
+                          if k in self.requested} for bf in self.bufs]
         self.s_copy, self.s_comp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.ev_h2d = [torch.cuda.Event() for _ in range(2)]
         self.ev_comp = [torch.cuda.Event() for _ in range(2)]
         self.ev_d2h = [torch.cuda.Event() for _ in range(2)]
         self.h2d_bytes_per_track = channels * self.n_samples * 4
-        self.d2h_bytes_per_chunk = self.bufs[0].bytes_d2h()
+        self.d2h_bytes_per_chunk = sum(t.numel() * t.element_size() for t in self.host_out[0].values())
         # partial final chunks reuse the full-size buffers with a shorter batch view
         self._ws = workspace(plan, self.batches[0])
 
@@ -415,8 +421,8 @@ class HostPipeline:
                 self.ev_comp[b].record(self.s_comp)
             with torch.cuda.stream(self.s_out):
                 self.s_out.wait_event(self.ev_comp[b])
-                for k, v in self.bufs[b].t.items():
-                    self.host_out[b][k].copy_(v, non_blocking=True)
+                for k, h in self.host_out[b].items():
+                    h.copy_(self.bufs[b].t[k], non_blocking=True)
                 self.ev_d2h[b].record(self.s_out)
             pending[b] = (ci, first, cnt)
         finish(n_chunks & 1)
