@@ -360,26 +360,35 @@ def ours(args, rank, world, local_rank):
     # (HPSS curves and true peak computed on the device, magnitude and tempogram never downloaded; NOT the contract's
     # e2e figure, which copies every frontend output back)
     e2e_analysis = None
+    d2h_full = n_chunks * d2h_chunk_full
     if not args.no_analysis_leg:
         del pipe
         torch.cuda.empty_cache()
-        pipe_a = engine.HostPipeline(plan, n, 2, chunk, engine.ANALYSIS_OUTPUTS)
-        pipe_a.run(tracks, consume)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            pipe_a.run(tracks, consume)
-        barrier()
-        ta = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
-        e2e_analysis = {"value": world * audio_per_step / float(ta.item()), "unit": UNIT, "s_per_step": float(ta.item()),
-                        "h2d_bytes_per_step": nt * 2 * n * 4, "d2h_bytes_per_step": n_chunks * pipe_a.d2h_bytes_per_chunk,
-                        "note": "outputs consumed by analyse_track's host stages (HPSS curves + true peak on the device; "
-                                "magnitude and tempogram stay in HBM)"}
-        d2h_full = n_chunks * d2h_chunk_full
-    else:
-        d2h_full = n_chunks * d2h_chunk_full
+        e2e_analysis = {"note": "outputs consumed by analyse_track's host stages (HPSS curves + true peak on the device; "
+                                "magnitude and tempogram stay in HBM); pcm16: host tracks are interleaved int16 as a 16-bit "
+                                "WAV stores them, decoded on the device"}
+        for label, pcm16 in (("f32_input", False), ("pcm16_input", True)):
+            src = tracks
+            if pcm16:
+                pool16 = [torch.from_numpy(np.ascontiguousarray(
+                    np.clip(np.round(t.numpy().reshape(2, n) * 32767.0), -32768, 32767).astype(np.int16).T).reshape(-1)).pin_memory()
+                    for t in host_pool]
+                src = [pool16[i % pool_n] for i in range(nt)]
+            pipe_a = engine.HostPipeline(plan, n, 2, chunk, engine.ANALYSIS_OUTPUTS, pcm16=pcm16)
+            pipe_a.run(src, consume)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                pipe_a.run(src, consume)
+            barrier()
+            ta = torch.tensor([(time.perf_counter() - t0) / e2e_steps], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+            e2e_analysis[label] = {"value": world * audio_per_step / float(ta.item()), "unit": UNIT, "s_per_step": float(ta.item()),
+                                   "h2d_bytes_per_step": nt * pipe_a.h2d_bytes_per_track,
+                                   "d2h_bytes_per_step": n_chunks * pipe_a.d2h_bytes_per_chunk}
+            del pipe_a
+            torch.cuda.empty_cache()
 
     if rank == 0:
         B = N_FFT // 2 + 1

@@ -185,6 +185,16 @@ TA_API int ta_time_domain(const ta_plan* plan, const ta_batch* batch, const ta_f
 TA_API int ta_chroma_stft(const ta_plan* plan, const ta_batch* batch, const float* magnitude, const float* frame_max,
                           float* chroma, double* tuning, void* workspace, size_t workspace_bytes, void* stream);
 
+/* K0: PCM decode on the device.  `interleaved` holds n_frames * channels samples as a WAV data chunk stores them
+ * (device pointer); planar_out receives (channels, n_frames) float32, the layout of io.load_audio (io.py:72-79) and of
+ * ta_batch.pcm.  Conversions are libsndfile's: int16 / 2^15, packed 24-bit / 2^23, int32 / 2^31, float32 copied. */
+#define TA_PCM_S16 1
+#define TA_PCM_S24 2
+#define TA_PCM_S32 3
+#define TA_PCM_F32 4
+TA_API int ta_decode_pcm(const void* interleaved, int format, int channels, int64_t n_frames, float* planar_out,
+                         void* stream);
+
 /* K9: per-frame sums of the harmonic and percussive components of librosa.decompose.hpss (31-wide median
  * filters along time and frequency, soft masks with power 2) on an existing magnitude spectrogram:
  * analysis/structure.py:52 as consumed at :143-144 and :212-213.  scratch: B * P floats. */

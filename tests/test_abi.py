@@ -18,7 +18,7 @@ def test_library_is_built_and_exports_header_symbols(repo_root):
     assert os.path.exists(_native.LIB_PATH), "run __graft_entry__.build() first"
     lib = ctypes.CDLL(_native.LIB_PATH)
     names = header_symbols(repo_root)
-    assert len(names) >= 17
+    assert len(names) >= 18
     for name in names:
         assert hasattr(lib, name), f"{name} declared in ta_b200.h but not exported"
     assert set(names) == set(_native.SYMBOLS), "binding table and header disagree"

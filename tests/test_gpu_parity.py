@@ -368,6 +368,61 @@ def test_tempo_api_like_reference_test():
     np.testing.assert_array_equal(grid["frame"].to_numpy(), ref_frames)
 
 
+# ------------------------------------------------------------------------------ PCM decode (K0) and the streaming pipeline
+@pytest.mark.parametrize("fmt", ["s16", "s24", "s32", "f32"])
+@pytest.mark.parametrize("channels", [1, 2])
+def test_decode_pcm_matches_libsndfile_conversion(fmt, channels):
+    rng = np.random.default_rng(7)
+    n = 10_007
+    if fmt == "s16":
+        raw = rng.integers(-32768, 32768, size=n * channels, dtype=np.int16)
+        ref = raw.astype(np.float32) / 32768.0
+        dev = torch.from_numpy(raw).cuda()
+    elif fmt == "s24":
+        v = rng.integers(-(1 << 23), 1 << 23, size=n * channels, dtype=np.int32)
+        b = np.stack([v & 0xFF, (v >> 8) & 0xFF, (v >> 16) & 0xFF], axis=1).astype(np.uint8).reshape(-1)
+        ref = v.astype(np.float32) / 8388608.0
+        dev = torch.from_numpy(b).cuda()
+    elif fmt == "s32":
+        raw = rng.integers(-(1 << 31), 1 << 31, size=n * channels, dtype=np.int64).astype(np.int32)
+        ref = (raw.astype(np.float64) / 2147483648.0).astype(np.float32)
+        dev = torch.from_numpy(raw).cuda()
+    else:
+        raw = rng.standard_normal(n * channels).astype(np.float32)
+        ref = raw
+        dev = torch.from_numpy(raw).cuda()
+    out = engine.decode_pcm(dev, fmt, channels).cpu().numpy()
+    np.testing.assert_array_equal(out, ref.reshape(n, channels).T)  # bit-exact: (channels, n) planar like io.py:79
+
+
+def test_host_pipeline_pcm16_equals_float_path():
+    sr = 44_100
+    plan = plan_for(sr)
+    x = [synth.synth_track(90 + i, 2.0, sr, 2) for i in range(5)]
+    pcm = [np.clip(np.round(t * 32767.0), -32768, 32767).astype(np.int16) for t in x]       # what a PCM16 WAV stores
+    as_float = [(q.astype(np.float32) / 32768.0) for q in pcm]
+    outs = ("mel", "onset_env", "lufs", "true_peak", "hpss_percussive")
+    n = x[0].shape[1]
+    ref = engine.analyse_batch(plan, as_float, outs)
+    pipe = engine.HostPipeline(plan, n, 2, 2, outs, pcm16=True)   # chunks of 2 tracks: 2 + 2 + 1
+    host = [torch.from_numpy(np.ascontiguousarray(q.T).reshape(-1)).pin_memory() for q in pcm]  # interleaved L R L R
+    got = {}
+
+    def consume(ci, first, cnt, out):
+        for j in range(cnt):
+            got[first + j] = {"lufs": float(out["lufs"][j]), "true_peak": float(out["true_peak"][j]),
+                              "onset_sum": float(out["onset_env"].numpy().reshape(-1)[j * pipe.batches[0].pitch[0]:][: ref[0].n_frames].sum())}
+
+    assert pipe.run(host, consume) == 3
+    torch.cuda.synchronize()
+    assert sorted(got) == [0, 1, 2, 3, 4]
+    for i, r in enumerate(ref):
+        assert got[i]["lufs"] == pytest.approx(r["lufs"], abs=1e-9)
+        assert got[i]["true_peak"] == pytest.approx(r["true_peak"], abs=1e-9)
+        assert got[i]["onset_sum"] == pytest.approx(float(np.sum(r["onset_env"], dtype=np.float32)), rel=1e-5)
+    assert pipe.h2d_bytes_per_track == 2 * n * 2
+
+
 # ------------------------------------------------------------------------------ C-ABI error behaviour
 def test_abi_errors():
     plan = plan_for(44_100)

@@ -20,6 +20,7 @@ TA_ERR_INVALID = -1
 TA_ERR_CUDA = -2
 TA_ERR_UNSUPPORTED = -3
 TA_ERR_WORKSPACE = -4
+TA_PCM_S16, TA_PCM_S24, TA_PCM_S32, TA_PCM_F32 = 1, 2, 3, 4
 
 
 class NativeError(RuntimeError):
@@ -102,6 +103,7 @@ SYMBOLS = {
     "ta_onset_flux": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ta_autocorrelate": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ta_chroma_stft": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ta_decode_pcm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "ta_hpss_curves": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ta_tempogram": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ta_time_domain": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(FrontendOut), C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -191,6 +191,23 @@ def upload(plan: Plan, tracks: Sequence[np.ndarray]) -> DeviceBatch:
     return DeviceBatch(plan, dev, offsets, n_samples, channels)
 
 
+PCM_FORMATS = {"s16": (nat.TA_PCM_S16, 2), "s24": (nat.TA_PCM_S24, 3), "s32": (nat.TA_PCM_S32, 4), "f32": (nat.TA_PCM_F32, 4)}
+
+
+def decode_pcm(raw: torch.Tensor, fmt: str, channels: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Interleaved PCM bytes already on the device (a WAV data chunk: uint8 / int16 / int32 / float32 tensor) ->
+    planar float32 ``(channels, n_frames)`` on the same device, by the library's decode kernel (io.py:72-79)."""
+    code, width = PCM_FORMATS[fmt]
+    nbytes = raw.numel() * raw.element_size()
+    n_frames = nbytes // (width * channels)
+    if out is None:
+        out = torch.empty((channels, n_frames), dtype=torch.float32, device=raw.device)
+    assert out.is_cuda and out.dtype == torch.float32 and out.numel() >= channels * n_frames
+    stream = C.c_void_p(torch.cuda.current_stream(raw.device).cuda_stream)
+    nat.check(nat.load().ta_decode_pcm(C.c_void_p(raw.data_ptr()), code, channels, n_frames, C.c_void_p(out.data_ptr()), stream))
+    return out
+
+
 class FrontendBuffers:
     """Device output buffers (torch-owned) for one DeviceBatch and the matching C struct."""
 
@@ -356,9 +373,15 @@ class HostPipeline:
     """
 
     def __init__(self, plan: Plan, n_samples: int, channels: int, chunk_tracks: int,
-                 outputs: Iterable[str] = ALL_OUTPUTS):
+                 outputs: Iterable[str] = ALL_OUTPUTS, pcm16: bool = False):
+        """``pcm16``: the host tracks are interleaved int16 PCM (what a 16-bit WAV file holds, n_samples * channels
+        values each); they are copied as such -- half the PCIe bytes -- and converted to planar float32 by the decode
+        kernel on the copy stream."""
         self.plan, self.n_samples, self.channels, self.chunk = plan, int(n_samples), int(channels), int(chunk_tracks)
+        self.pcm16 = bool(pcm16)
         dev = torch.device(f"cuda:{plan.device}")
+        self.dev_raw = ([torch.empty(self.chunk * channels * self.n_samples, dtype=torch.int16, device=dev) for _ in range(2)]
+                        if self.pcm16 else None)
         self.stride = (channels * self.n_samples + 3) & ~3
         offsets = np.arange(self.chunk, dtype=np.int64) * self.stride
         ns = np.full(self.chunk, self.n_samples, dtype=np.int64)
@@ -374,7 +397,7 @@ class HostPipeline:
         self.ev_h2d = [torch.cuda.Event() for _ in range(2)]
         self.ev_comp = [torch.cuda.Event() for _ in range(2)]
         self.ev_d2h = [torch.cuda.Event() for _ in range(2)]
-        self.h2d_bytes_per_track = channels * self.n_samples * 4
+        self.h2d_bytes_per_track = channels * self.n_samples * (2 if self.pcm16 else 4)
         self.d2h_bytes_per_chunk = sum(t.numel() * t.element_size() for t in self.host_out[0].values())
         # partial final chunks reuse the full-size buffers with a shorter batch view
         self._ws = workspace(plan, self.batches[0])
@@ -406,9 +429,15 @@ class HostPipeline:
             cnt = min(self.chunk, n - first)
             with torch.cuda.stream(self.s_copy):
                 self.s_copy.wait_event(self.ev_comp[b])
+                per = self.channels * self.n_samples
                 for j in range(cnt):
-                    self.dev_in[b][j * self.stride: j * self.stride + host_tracks[first + j].numel()].copy_(
-                        host_tracks[first + j], non_blocking=True)
+                    if self.pcm16:
+                        raw = self.dev_raw[b][j * per: (j + 1) * per]
+                        raw.copy_(host_tracks[first + j], non_blocking=True)
+                        decode_pcm(raw, "s16", self.channels, out=self.dev_in[b][j * self.stride: j * self.stride + per])
+                    else:
+                        self.dev_in[b][j * self.stride: j * self.stride + host_tracks[first + j].numel()].copy_(
+                            host_tracks[first + j], non_blocking=True)
                 self.ev_h2d[b].record(self.s_copy)
             with torch.cuda.stream(self.s_comp):
                 self.s_comp.wait_event(self.ev_h2d[b])
