@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define TA_ABI_VERSION 2
+#define TA_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define TA_API __attribute__((visibility("default")))
@@ -52,6 +52,7 @@ extern "C" {
 #define TA_ERR_WORKSPACE (-4) /* workspace too small */
 
 #define TA_N_MOMENTS 10      /* doubles per track in ta_frontend_out.moments */
+#define TA_N_MFCC 13         /* cepstral coefficients per frame in ta_frontend_out.mfcc (structure.py:199) */
 
 typedef struct ta_plan ta_plan;
 
@@ -128,6 +129,8 @@ typedef struct ta_frontend_out {
     float* hpss_harmonic;  /* [P]      sum over bins of librosa.decompose.hpss(magnitude)[0]: structure.py:52,143,213 */
     float* hpss_percussive;/* [P]      same for the percussive component (structure.py:144,212) */
     float* hpss_scratch;   /* [B * P]  caller-provided scratch (time-direction medians); required with the two above */
+    double* mfcc;          /* [TA_N_MFCC * P] librosa.feature.mfcc(S=power_to_db(mel + 1e-9), n_mfcc=13), float64:
+                              analysis/structure.py:192,199 (needs mel) */
     int32_t kw_pitch;      /* capacity per track of kw_blocks */
     int32_t rms_pitch;     /* capacity per track of rms_momentary / rms_short */
 } ta_frontend_out;

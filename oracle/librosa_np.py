@@ -192,6 +192,14 @@ def power_to_db(S, ref=1.0, amin=1e-10, top_db=80.0):
     return log_spec
 
 
+def mfcc(S, n_mfcc=13):
+    """librosa.feature.mfcc(S=log_power_mel, n_mfcc=13, dct_type=2, norm="ortho", lifter=0) as called at
+    analysis/structure.py:199: the first n_mfcc rows of the orthonormal DCT-II along the mel axis."""
+    import scipy.fft
+
+    return scipy.fft.dct(np.asarray(S), axis=-2, type=2, norm="ortho")[..., :n_mfcc, :]
+
+
 def amplitude_to_db(S, ref=1.0, amin=1e-5, top_db=80.0):
     magnitude = np.abs(np.asarray(S))
     power = np.square(magnitude)

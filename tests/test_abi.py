@@ -33,7 +33,7 @@ def test_abi_version_and_error_string():
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_native.PlanDesc) == 8 * 4 + 4 * 8
     assert ctypes.sizeof(_native.Batch) == 8 + 3 * 8
-    assert ctypes.sizeof(_native.FrontendOut) == 22 * 8 + 8
+    assert ctypes.sizeof(_native.FrontendOut) == 23 * 8 + 8
 
 
 def test_no_cpu_fallback_without_device():

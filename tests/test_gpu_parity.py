@@ -567,6 +567,24 @@ def test_hpss_curves_match_oracle(sr, seconds, channels):
                                    rtol=RTOL, atol=1e-5 * scale)
 
 
+def test_mfcc_matches_oracle_and_ragged_batch():
+    """K10: float64 cepstrum of power_to_db(mel + 1e-9) (analysis/structure.py:192,199)."""
+    sr = 44_100
+    a, b, c = synth.synth_track(83, 6.0, sr, 2), synth.synth_track(84, 0.7, sr, 2), np.zeros((2, 3000), np.float32)
+    res = engine.analyse_batch(plan_for(sr), [a, b, c], ("mfcc", "mel"))
+    for r, x in zip(res, (a, b, c)):
+        mono = np.mean(x, axis=0)
+        assert r["mfcc"].shape == (13, 1 + x.shape[1] // 512) and r["mfcc"].dtype == np.float64
+        # the kernel's own arithmetic, on the mel matrix it consumed: float64 round-off only
+        own = olr.mfcc(olr.power_to_db(np.asarray(r["mel"], dtype=float) + 1e-9))
+        np.testing.assert_allclose(r["mfcc"], own, rtol=1e-10, atol=1e-9)
+        # end to end against the oracle's mel (float32 spectra within rtol 1e-4 => dB within 4.4e-4 per band)
+        mel = olr.melspectrogram(mono, sr, n_fft=2048, hop_length=512, n_mels=128)
+        ref = olr.mfcc(olr.power_to_db(np.asarray(mel, dtype=float) + 1e-9))
+        np.testing.assert_allclose(r["mfcc"], ref, rtol=RTOL, atol=5e-3)
+    np.testing.assert_allclose(res[2]["mfcc"][1:], 0.0, atol=1e-9)  # silence: flat log-mel, only the DC row is non-zero
+
+
 def test_hpss_short_track_multiple_reflections():
     sr = 44_100
     x = synth.synth_track(82, 0.1, sr, 1)  # T = 9 frames < 31: scipy's reflect border wraps more than once

@@ -176,3 +176,24 @@ def test_harmony_host_logic_on_oracle_chroma():
     assert midi.notes["pitch"].between(48, 59).all() and midi.notes["velocity"].between(20, 127).all()
     assert len(harmony._chord_templates()) == 60
     assert harmony._score_keys([])[0].size == 0 and harmony._rank_keys(np.array([]), []).best.key == "C major"
+
+
+def test_vectorised_chord_estimate_equals_per_template_loop():
+    """harmony._estimate_chords scores all templates with one matrix product; it must reproduce the reference's
+    per-template np.dot loop (harmony.py:305-312) exactly, including the seeded tie-breaker draws."""
+    from types import SimpleNamespace
+    from track_analyser_b200 import harmony
+
+    rng0 = np.random.default_rng(3)
+    chroma = rng0.random((12, 3000)).astype(np.float32)
+    frames = sorted(set(rng0.integers(0, 3000, size=300).tolist()))
+    br = SimpleNamespace(beat_frames=frames, beat_times=[f * 512 / 44100 for f in frames])
+    names, mats = zip(*harmony._chord_templates().items())
+    rng = np.random.default_rng(7)
+    want = []
+    for idx, profile in harmony._beat_profiles(chroma, br):
+        scores = np.array([float(np.dot(t, profile)) for t in mats])
+        best = int(np.argmax(scores + rng.normal(0.0, 1e-6, size=scores.shape)))
+        want.append((float(br.beat_times[idx]), names[best], float(scores[best] / float(np.max(scores + 1e-9)))))
+    got = [(h.time, h.chord, h.confidence) for h in harmony._estimate_chords(chroma, br, np.random.default_rng(7))]
+    assert got == want and len(got) > 250

@@ -14,7 +14,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libta_b200.so")
 
-TA_ABI_VERSION = 2
+TA_ABI_VERSION = 3
 TA_OK = 0
 TA_ERR_INVALID = -1
 TA_ERR_CUDA = -2
@@ -82,6 +82,7 @@ class FrontendOut(C.Structure):
         ("hpss_harmonic", C.c_void_p),
         ("hpss_percussive", C.c_void_p),
         ("hpss_scratch", C.c_void_p),
+        ("mfcc", C.c_void_p),
         ("kw_pitch", C.c_int32),
         ("rms_pitch", C.c_int32),
     ]

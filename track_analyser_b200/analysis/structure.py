@@ -42,12 +42,13 @@ class StructureAnalysis:
 
 @dataclass(slots=True)
 class StructureFrontend:
-    magnitude: np.ndarray      # (1 + n_fft/2, T) float32  -- structure.py:48-51
-    mel: np.ndarray            # (128, T) float32 power    -- structure.py:53-59
-    log_mel: np.ndarray        # (128, T) float64          -- structure.py:194
-    spectral_flux: np.ndarray  # (T,) float64              -- structure.py:195-196
+    magnitude: np.ndarray | None  # (1 + n_fft/2, T) float32  -- structure.py:48-51 (None: left on the device)
+    mel: np.ndarray | None        # (128, T) float32 power    -- structure.py:53-59 (None: left on the device)
+    log_mel: np.ndarray | None    # (128, T) float64          -- structure.py:192
+    spectral_flux: np.ndarray     # (T,) float64              -- structure.py:193-194
     harmonic_curve: np.ndarray | None = None    # (T,) sum over bins of hpss(magnitude)[0]
     percussive_curve: np.ndarray | None = None  # (T,) sum over bins of hpss(magnitude)[1]
+    mfcc: np.ndarray | None = None              # (13, T) float64 mfcc(S=log_mel) from csrc/mfcc.cu -- structure.py:199
 
 
 def power_to_db(S: np.ndarray, amin: float = 1e-10, top_db: float = 80.0) -> np.ndarray:
@@ -58,16 +59,26 @@ def power_to_db(S: np.ndarray, amin: float = 1e-10, top_db: float = 80.0) -> np.
 
 
 def structure_frontend(audio: AudioInput, *, frame_length: int = 2048, hop_length: int = 512,
-                       magnitude: bool = True) -> StructureFrontend:
+                       magnitude: bool = True, matrices: bool = True) -> StructureFrontend:
+    """Device outputs the structure stage consumes.  ``matrices=False`` (what analyse_structure uses) leaves the
+    (128, T) mel matrix in HBM as well and brings back its 13-row cepstrum instead."""
     if not isinstance(audio, AudioInput):
         raise TypeError("analyse_structure expects an AudioInput instance")
-    outs = ("mel", "flux_linear", "hpss_harmonic", "hpss_percussive") + (("magnitude",) if magnitude else ())
+    outs = ("flux_linear", "hpss_harmonic", "hpss_percussive", "mfcc") + (("mel",) if matrices else ()) + \
+           (("magnitude",) if magnitude else ())
     res = runtime.frontend(np.asarray(audio.samples, dtype=np.float32), audio.sample_rate, n_fft=frame_length,
                            hop=hop_length, outputs=outs)
+    if not matrices:
+        return StructureFrontend(magnitude=res["magnitude"] if (magnitude and "magnitude" in res) else None, mel=None,
+                                 log_mel=None, spectral_flux=np.asarray(res["flux_linear"], dtype=float),
+                                 harmonic_curve=np.asarray(res["hpss_harmonic"]), percussive_curve=np.asarray(res["hpss_percussive"]),
+                                 mfcc=np.asarray(res["mfcc"]))
     mel64 = np.asarray(res["mel"], dtype=float)
-    return StructureFrontend(magnitude=res["magnitude"] if "magnitude" in res else None, mel=res["mel"],
+    # inside a session the fused run holds every output; the 64 MB magnitude is only copied back when asked for
+    return StructureFrontend(magnitude=res["magnitude"] if (magnitude and "magnitude" in res) else None, mel=res["mel"],
                              log_mel=power_to_db(mel64 + 1e-9), spectral_flux=np.asarray(res["flux_linear"], dtype=float),
-                             harmonic_curve=np.asarray(res["hpss_harmonic"]), percussive_curve=np.asarray(res["hpss_percussive"]))
+                             harmonic_curve=np.asarray(res["hpss_harmonic"]), percussive_curve=np.asarray(res["hpss_percussive"]),
+                             mfcc=np.asarray(res["mfcc"]))
 
 
 # ------------------------------------------------------------------------------ host logic (structure.py:61-342)
@@ -78,12 +89,16 @@ def _unit_range(curve: np.ndarray) -> np.ndarray:
     return np.zeros_like(curve) if hi - lo < 1e-9 else (curve - lo) / (hi - lo)
 
 
-def novelty_curves(log_mel: np.ndarray, spectral_flux: np.ndarray, percussive_curve: np.ndarray, harmonic_curve: np.ndarray,
-                   *, hop_length: int, sample_rate: int, context_seconds: float = 2.0) -> Tuple[np.ndarray, np.ndarray]:
-    """(smoothed combined novelty, normalised energy novelty): structure.py:182-224 from the device curves."""
-    frames = log_mel.shape[1]
-    # librosa.feature.mfcc(S=log_mel, n_mfcc=13): orthonormal DCT-II along the mel axis, first 13 rows
-    mfcc = scipy.fft.dct(np.asarray(log_mel, dtype=float), axis=0, type=2, norm="ortho")[:13]
+def novelty_curves(log_mel: np.ndarray | None, spectral_flux: np.ndarray, percussive_curve: np.ndarray,
+                   harmonic_curve: np.ndarray, *, hop_length: int, sample_rate: int, context_seconds: float = 2.0,
+                   mfcc: np.ndarray | None = None) -> Tuple[np.ndarray, np.ndarray]:
+    """(smoothed combined novelty, normalised energy novelty): structure.py:182-224 from the device curves.
+
+    ``mfcc``: the (13, T) cepstrum when it was already formed (on the device); else it is derived from log_mel."""
+    if mfcc is None:
+        # librosa.feature.mfcc(S=log_mel, n_mfcc=13): orthonormal DCT-II along the mel axis, first 13 rows
+        mfcc = scipy.fft.dct(np.asarray(log_mel, dtype=float), axis=0, type=2, norm="ortho")[:13]
+    frames = mfcc.shape[1]
     mfcc = scipy.ndimage.gaussian_filter1d(mfcc, sigma=1.0, axis=1)
     context = max(2, int(round(context_seconds * sample_rate / float(hop_length))))
     self_similarity = np.zeros(frames, dtype=float)
@@ -187,10 +202,12 @@ def boundaries_from_curves(novelty: np.ndarray, energy_novelty: np.ndarray, beat
 
 def segments_from_curves(frontend: StructureFrontend, beat_result: BeatAnalysis, *, sample_rate: int, hop_length: int,
                          duration: float) -> StructureAnalysis:
-    if frontend.mel.size == 0:
+    if (frontend.mel if frontend.mel is not None else frontend.mfcc).size == 0:
         raise ValueError("not enough values to unpack (expected 2, got 0)")  # the reference's behaviour on empty audio
+    # the cepstrum computed next to the mel matrix on the device is used when the matrix itself stayed there
     novelty, energy_novelty = novelty_curves(frontend.log_mel, frontend.spectral_flux, frontend.percussive_curve,
-                                             frontend.harmonic_curve, hop_length=hop_length, sample_rate=sample_rate)
+                                             frontend.harmonic_curve, hop_length=hop_length, sample_rate=sample_rate,
+                                             mfcc=frontend.mfcc if frontend.log_mel is None else None)
     frames, times = boundaries_from_curves(novelty, energy_novelty, beat_result.beat_times, sample_rate=sample_rate,
                                            hop_length=hop_length)
     labels = [chr(ord("A") + i % 26) for i in range(len(frames) - 1)]
@@ -219,6 +236,6 @@ def analyse_structure(audio: AudioInput | str, beat_result: BeatAnalysis, *, see
     if not isinstance(audio, AudioInput):
         raise TypeError("analyse_structure expects an AudioInput instance")
     seed_everything(seed)
-    fe = structure_frontend(audio, frame_length=frame_length, hop_length=hop_length, magnitude=False)
+    fe = structure_frontend(audio, frame_length=frame_length, hop_length=hop_length, magnitude=False, matrices=False)
     return segments_from_curves(fe, beat_result, sample_rate=audio.sample_rate, hop_length=hop_length,
                                 duration=float(audio.duration))

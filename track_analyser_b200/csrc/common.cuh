@@ -60,6 +60,7 @@ struct ta_plan {
     int* d_mel_woff = nullptr;  // [n_mels]
     float* d_mel_w = nullptr;   // [nnz]
     int mel_nnz = 0;
+    double* d_dct = nullptr;    // [TA_N_MFCC * n_mels] orthonormal DCT-II rows (K10)
     float2* d_tg_tw1 = nullptr;   // tempogram transform (N = 1024) twiddles and window
     float2* d_tg_tw2 = nullptr;
     float* d_tg_window = nullptr;

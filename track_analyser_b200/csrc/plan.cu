@@ -168,6 +168,15 @@ static int plan_build(ta_plan* p) {
         if ((rc = upload(&p->d_mel_len, len))) return rc;
         if ((rc = upload(&p->d_mel_woff, woff))) return rc;
         if ((rc = upload(&p->d_mel_w, w))) return rc;
+        // scipy.fft.dct(type=2, norm="ortho") rows 0..12 over the mel axis (librosa.feature.mfcc)
+        const int M = p->desc.n_mels;
+        std::vector<double> dct(size_t(TA_N_MFCC) * M);
+        const double pi = 3.14159265358979323846;
+        for (int k = 0; k < TA_N_MFCC; ++k)
+            for (int m = 0; m < M; ++m)
+                dct[size_t(k) * M + m] = k == 0 ? 1.0 / std::sqrt(double(M))
+                                                : std::sqrt(2.0 / M) * std::cos(pi * k * (2 * m + 1) / (2.0 * M));
+        if ((rc = upload(&p->d_dct, dct))) return rc;
         p->mel_nnz = int(w.size());
     }
 
@@ -315,6 +324,8 @@ size_t chroma_scratch_bytes(const ta_plan* plan, const HostBatch& hb);
 int run_chroma(const ta_plan*, const HostBatch&, const TrackDesc*, const float* mag, const float* frame_max, float* chroma,
                double* tuning, void* scratch, size_t scratch_bytes, cudaStream_t);
 int run_tempogram(const ta_plan*, const HostBatch&, const TrackDesc*, const float* env, float* out, cudaStream_t);
+int run_mfcc(const ta_plan*, const HostBatch&, const TrackDesc*, const float* mel, const uint32_t* mel_max, double* mfcc,
+             cudaStream_t);
 int run_hpss(const ta_plan*, const HostBatch&, const TrackDesc*, const float* mag, float* scratch, float* harm_sum, float* perc_sum,
              cudaStream_t);
 
@@ -399,6 +410,7 @@ void ta_plan_destroy(ta_plan* p) {
     cudaFree(p->d_mel_woff);
     if (p->aux_stream) cudaStreamDestroy(p->aux_stream);
     cudaFree(p->d_mel_w);
+    cudaFree(p->d_dct);
     cudaFree(p->d_tg_tw1);
     cudaFree(p->d_tg_tw2);
     cudaFree(p->d_tg_window);
@@ -593,6 +605,10 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
                                           out->flux_linear, st)) != TA_OK) {
         join();
         return rc;
+    }
+    if (out->mfcc) {
+        if (!out->mel) { join(); set_error("mfcc output needs the mel output buffer"); return TA_ERR_INVALID; }
+        if ((rc = run_mfcc(plan, hb, ws.d_tracks, out->mel, ws.d_mel_max, out->mfcc, st)) != TA_OK) { join(); return rc; }
     }
     mark(2);
     if (out->autocorr &&

@@ -10,7 +10,10 @@ planar float32 arrays processed by one launch sequence.
 from __future__ import annotations
 
 import ctypes as C
+import os
+import sys
 import threading
+import time
 from dataclasses import dataclass, field
 from typing import Iterable, Sequence
 
@@ -19,22 +22,25 @@ import torch
 
 from . import _native as nat
 
+_TRACE_FETCH = os.environ.get("TA_TRACE_FETCH", "0") not in ("", "0")  # debugging aid: log every lazy D2H fetch
+
 ALL_OUTPUTS = (
     "magnitude", "mel", "onset_env", "autocorr", "flux_linear", "ltas", "centroid", "rolloff_bin",
     "band_energy", "moments", "kw_blocks", "lufs", "rms_momentary", "rms_short", "frame_max", "chroma", "tuning",
-    "tempogram", "true_peak", "hpss_harmonic", "hpss_percussive",
+    "tempogram", "true_peak", "hpss_harmonic", "hpss_percussive", "mfcc",
 )
-# SURVEY section 8a (the north-star frontend): what bench.py measures.  true_peak and the HPSS curves are
+# SURVEY section 8a (the north-star frontend): what bench.py measures.  true_peak, the HPSS curves and the MFCC are
 # section-8f "next" rows.
-FRONTEND_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o not in ("true_peak", "hpss_harmonic", "hpss_percussive"))
-# What the host-side stages of pipeline.analyse_track consume: neither the magnitude (HPSS runs on the device) nor the
-# plot-only tempogram leave the GPU.
-ANALYSIS_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o not in ("magnitude", "tempogram"))
+FRONTEND_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o not in ("true_peak", "hpss_harmonic", "hpss_percussive", "mfcc"))
+# What the host-side stages of pipeline.analyse_track consume: neither the magnitude (HPSS runs on the device), nor the
+# mel matrix (its only host consumer, the MFCC, runs on the device) nor the plot-only tempogram leave the GPU.
+ANALYSIS_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o not in ("magnitude", "mel", "tempogram"))
 # the bench / default frontend: everything the per-track analysis consumes except the plot-only tempogram
 CORE_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o != "tempogram")
 DEFAULT_OUTPUTS = tuple(o for o in CORE_OUTPUTS if o != "magnitude")
 
 
+N_MFCC = 13     # TA_N_MFCC
 N_MOMENTS = 10  # TA_N_MOMENTS: sum L, R, L^2, R^2, LR, mid^2, side^2, n, sum |L|, sum |R|
 STAGE_NAMES = ("stft_mel_features", "onset_flux", "autocorrelation", "tempogram", "chroma_stft", "time_domain_loudness")
 
@@ -145,6 +151,14 @@ class DeviceBatch:
                                  self.offsets.ctypes.data_as(C.POINTER(C.c_int64)),
                                  self.n_samples.ctypes.data_as(C.POINTER(C.c_int64)))
 
+    def rebind(self, plan: Plan) -> "DeviceBatch":
+        """The same resident PCM described for another plan (frame counts and pitches follow the plan's hop)."""
+        if plan is self.plan:
+            return self
+        if plan.device != self.plan.device:
+            raise ValueError("the batch lives on another device than the plan")
+        return DeviceBatch(plan, self.pcm, self.offsets, self.n_samples, self.channels)
+
 
 _staging: dict = {}
 _staging_lock = threading.Lock()
@@ -219,7 +233,7 @@ class FrontendBuffers:
         unknown = outputs - set(ALL_OUTPUTS)
         if unknown:
             raise ValueError(f"unknown outputs {sorted(unknown)}")
-        if outputs & {"onset_env", "autocorr", "flux_linear"}:
+        if outputs & {"onset_env", "autocorr", "flux_linear", "mfcc"}:
             outputs.add("mel")
         if outputs & {"autocorr", "tempogram"}:
             outputs.add("onset_env")
@@ -245,6 +259,7 @@ class FrontendBuffers:
             "frame_max": ((P,), torch.float32), "chroma": ((12 * P,), torch.float32), "tuning": ((nt,), torch.float64),
             "tempogram": ((plan.tempogram_win * P,), torch.float32), "true_peak": ((nt,), torch.float32),
             "hpss_harmonic": ((P,), torch.float32), "hpss_percussive": ((P,), torch.float32),
+            "mfcc": ((N_MFCC * P,), torch.float64),
         }
         self.t = {k: torch.empty(shapes[k][0], dtype=shapes[k][1], device=dev) for k in ALL_OUTPUTS if k in outputs}
         self.c_out = nat.FrontendOut()
@@ -307,6 +322,8 @@ def _cut(plan: Plan, batch: DeviceBatch, i: int, k: str, h: np.ndarray):
     if k == "tempogram":
         W = plan.tempogram_win
         return h[W * po: W * (po + ld)].reshape(W, ld)[:, :T]
+    if k == "mfcc":
+        return h[N_MFCC * po: N_MFCC * (po + ld)].reshape(N_MFCC, ld)[:, :T]
     if k in ("tuning", "lufs", "true_peak"):
         return float(h[i])
     if k in ("onset_env", "autocorr", "flux_linear", "centroid", "rolloff_bin", "frame_max", "hpss_harmonic",
@@ -343,7 +360,11 @@ def lazy_results(batch: DeviceBatch, bufs: FrontendBuffers) -> list[TrackResult]
 
     def fetch(k):
         if k not in host:
+            t0 = time.perf_counter() if _TRACE_FETCH else 0.0
             host[k] = bufs.t[k].cpu().numpy()
+            if _TRACE_FETCH:
+                print(f"[ta fetch] {k}: {host[k].nbytes} B in {(time.perf_counter() - t0) * 1e3:.2f} ms (n_fft {plan.n_fft})",
+                      file=sys.stderr)
         return host[k]
 
     out = []
@@ -354,9 +375,12 @@ def lazy_results(batch: DeviceBatch, bufs: FrontendBuffers) -> list[TrackResult]
 
 
 def analyse_batch(plan: Plan, tracks: Sequence[np.ndarray], outputs: Iterable[str] = DEFAULT_OUTPUTS,
-                  lazy: bool = False) -> list[TrackResult]:
-    """Host arrays in, host results out: H2D copy, fused frontend, D2H copy (on first access with ``lazy``)."""
-    batch = upload(plan, tracks)
+                  lazy: bool = False, resident: DeviceBatch | None = None) -> list[TrackResult]:
+    """Host arrays in, host results out: H2D copy, fused frontend, D2H copy (on first access with ``lazy``).
+
+    ``resident``: a DeviceBatch that already holds exactly these tracks (uploaded for another plan); its PCM is
+    reused instead of being packed and copied again."""
+    batch = upload(plan, tracks) if resident is None else resident.rebind(plan)
     bufs = FrontendBuffers(batch, outputs)
     run_device(plan, batch, bufs)
     return lazy_results(batch, bufs) if lazy else download(batch, bufs)

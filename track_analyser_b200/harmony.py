@@ -220,24 +220,34 @@ def _chord_templates() -> Dict[str, np.ndarray]:
     return out
 
 
-def _estimate_chords(chroma: np.ndarray, beat_result: BeatAnalysis, rng: np.random.Generator) -> List[ChordHint]:
+def _estimate_chords(chroma: np.ndarray, beat_result: BeatAnalysis, rng: np.random.Generator, profiles=None) -> List[ChordHint]:
     if not beat_result.beat_frames:
         return []
     names, mats = zip(*_chord_templates().items())
     mats = np.stack(mats)
-    hints = []
-    for idx, profile in _beat_profiles(chroma, beat_result):
-        scores = np.array([float(np.dot(t, profile)) for t in mats])
-        best = int(np.argmax(scores + rng.normal(0.0, 1e-6, size=scores.shape)))  # seeded tie-breaker like the reference
-        hints.append(ChordHint(time=float(beat_result.beat_times[idx]), chord=names[best],
-                               confidence=float(scores[best] / float(np.max(scores + 1e-9)))))
-    return hints
+    prof = _beat_profiles(chroma, beat_result) if profiles is None else profiles
+    if not prof:
+        return []
+    # the reference scores one template at a time with np.dot (harmony.py:305-312); one matrix product gives the same
+    # 60 numbers per beat, and is used only if it reproduces np.dot bit for bit on this BLAS (checked on two beats)
+    P = np.stack([p for _, p in prof])
+    S = P @ mats.T
+    for r in {0, len(prof) - 1}:
+        if not np.array_equal(S[r], np.array([float(np.dot(t, P[r])) for t in mats])):
+            S = np.array([[float(np.dot(t, p)) for t in mats] for p in P])
+            break
+    noise = rng.normal(0.0, 1e-6, size=S.shape)  # row i is the reference's i-th draw (seeded tie-breaker)
+    best = np.argmax(S + noise, axis=1)
+    top = np.max(S + 1e-9, axis=1)
+    return [ChordHint(time=float(beat_result.beat_times[idx]), chord=names[int(b)], confidence=float(S[r, b] / float(top[r])))
+            for r, ((idx, _), b) in enumerate(zip(prof, best))]
 
 
-def _detect_chord_changes(chroma: np.ndarray, beat_result: BeatAnalysis, chord_hints: Sequence[ChordHint]) -> List[ChordChangePoint]:
+def _detect_chord_changes(chroma: np.ndarray, beat_result: BeatAnalysis, chord_hints: Sequence[ChordHint],
+                          profiles=None) -> List[ChordChangePoint]:
     if len(beat_result.beat_frames) < 2:
         return []
-    prof = _beat_profiles(chroma, beat_result)
+    prof = _beat_profiles(chroma, beat_result) if profiles is None else profiles
     if len(prof) < 2:
         return []
     times = [float(beat_result.beat_times[i]) for i, _ in prof]
@@ -300,8 +310,9 @@ def analyse_harmony(audio: AudioInput, beat_result: BeatAnalysis, downbeat_resul
         cqt_like = _chroma_cqt(audio.samples, audio.sample_rate)
         stft_chroma = chroma_stft(audio.samples, audio.sample_rate)[0]
     keys = _rank_keys(*_score_keys([cqt_like, stft_chroma]))
-    hints = _estimate_chords(cqt_like, beat_result, rng)
-    changes = _detect_chord_changes(cqt_like, beat_result, hints)
+    profiles = _beat_profiles(cqt_like, beat_result)  # shared by the two consumers (the reference builds them twice)
+    hints = _estimate_chords(cqt_like, beat_result, rng, profiles)
+    changes = _detect_chord_changes(cqt_like, beat_result, hints, profiles)
     if downbeat_result and downbeat_result.downbeat_times:
         offset = downbeat_result.downbeat_times[0]
     else:

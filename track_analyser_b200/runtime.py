@@ -63,8 +63,16 @@ def alias_mono_to_stereo(mono: np.ndarray, stereo: np.ndarray) -> bool:
         return False
     if mono.dtype != np.float32 or stereo.dtype != np.float32:
         return False
-    if not np.array_equal(np.mean(stereo, axis=0), mono):
-        return False
+    # np.mean over two float32 rows is (left + right) / 2 in float32; halving is exact, so it is compared as
+    # (left + right) * 0.5 in cache-sized pieces instead of materialising the full mean
+    tmp = np.empty(min(mono.shape[0], 1 << 18), dtype=np.float32)
+    for a in range(0, mono.shape[0], tmp.shape[0]):
+        b = min(mono.shape[0], a + tmp.shape[0])
+        t = tmp[: b - a]
+        np.add(stereo[0, a:b], stereo[1, a:b], out=t)
+        t *= np.float32(0.5)
+        if not np.array_equal(t, mono[a:b]):
+            return False
     cache.setdefault("__alias__", {})[_fingerprint(mono)] = _fingerprint(stereo)
     cache.setdefault("__alias_buf__", {})[_fingerprint(stereo)] = stereo
     return True
@@ -98,8 +106,14 @@ def frontend(samples: np.ndarray, sample_rate: int, *, n_fft: int = 2048, hop: i
         outs = tuple(o for o in outs if o not in ("kw_blocks", "lufs"))
     if want is None:  # "everything" means everything this plan can produce
         if n_mels == 0:
-            outs = tuple(o for o in outs if o not in ("mel", "onset_env", "autocorr", "flux_linear", "tempogram"))
-    res = engine.analyse_batch(plan, [x], outs, lazy=cache is not None)[0]
+            outs = tuple(o for o in outs if o not in ("mel", "onset_env", "autocorr", "flux_linear", "tempogram", "mfcc"))
+    resident = None
+    if cache is not None:  # the PCM of this buffer may already be in HBM for another plan of the same session
+        pcm_key = ("__pcm__", _fingerprint(x), plan.device)
+        resident = cache.get(pcm_key)
+        if resident is None:
+            resident = cache[pcm_key] = engine.upload(plan, [x])
+    res = engine.analyse_batch(plan, [x], outs, lazy=cache is not None, resident=resident)[0]
     if cache is not None:
         cache[key] = res
     return res

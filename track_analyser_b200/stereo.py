@@ -101,7 +101,10 @@ def width_from_band_energy(band_energy, freqs, n_frames, bands, sample_rate, mom
 
 
 def _as_pair(stereo: np.ndarray) -> np.ndarray:
-    left, right = np.asarray(stereo, dtype=np.float32)
+    a = np.asarray(stereo, dtype=np.float32)
+    if a.ndim == 2 and a.shape[0] == 2 and a.flags.c_contiguous:
+        return a  # already the planar pair: keep the buffer so a frontend session recognises it
+    left, right = a  # same unpacking (and the same ValueError for anything but two rows) as stereo.py:62
     return np.ascontiguousarray(np.stack([left, right]))
 
 
