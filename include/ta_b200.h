@@ -209,6 +209,20 @@ TA_API int ta_hpss_curves(const ta_plan* plan, const ta_batch* batch, const floa
 TA_API int ta_tempogram(const ta_plan* plan, const ta_batch* batch, const float* onset_env, float* tempogram,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* K11: resampy.resample(x, sr_orig, sr_new) (band-limited sinc interpolation, "kaiser_best") as the reference calls
+ * it per channel from utils._resample (utils.py:55-70) and load_audio (io.py:126-128).  The caller supplies the
+ * right half of the interpolation window (float64, n_window = num_zeros * num_table + 1 samples, num_table per
+ * zero crossing; resampy.filters.sinc_window) as a HOST array; the resampler keeps its scaled copy on the device.
+ * ta_resample converts n_rows planar rows of n_in samples (device, row pitch src_pitch) into rows of
+ * ta_resampler_out_len(n_in) = int(n_in * sr_new / sr_orig) samples. */
+typedef struct ta_resampler ta_resampler;
+TA_API int ta_resampler_create(int device, int sr_orig, int sr_new, const double* half_window, int n_window, int num_table,
+                               ta_resampler** out);
+TA_API void ta_resampler_destroy(ta_resampler* resampler);
+TA_API int64_t ta_resampler_out_len(const ta_resampler* resampler, int64_t n_in);
+TA_API int ta_resample(const ta_resampler* resampler, const float* src, int64_t n_in, int64_t src_pitch, int n_rows, float* dst,
+                       int64_t dst_pitch, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -705,3 +705,58 @@ def test_analyse_track_pipeline_like_reference():
     assert 0 < launches <= 70
     with pytest.raises(TypeError):
         harmony.harmony_frontend("not audio")
+
+
+@pytest.mark.parametrize("sr_orig,sr_new,n", [(48_000, 44_100, 30_000), (22_050, 44_100, 9_001), (44_100, 48_000, 12_345),
+                                              (96_000, 44_100, 20_000), (8_000, 44_100, 700), (48_000, 44_100, 5)])
+def test_resample_bit_exact_against_resampy_restatement(sr_orig, sr_new, n):
+    """K11 (utils.py:55-70): band-limited sinc interpolation, every tap in the reference implementation's order."""
+    from oracle import resampy_np
+    from track_analyser_b200 import resample as rs
+
+    rng = np.random.default_rng(n)
+    t = np.arange(n) / sr_orig
+    x = (0.4 * np.sin(2 * np.pi * 997.0 * t) + 0.05 * rng.standard_normal(n)).astype(np.float32)
+    st = np.stack([x, np.roll(x, 3) * np.float32(0.5)])
+    want = resampy_np.resample(x, sr_orig, sr_new)
+    got = rs.resample(x, sr_orig, sr_new)
+    assert got.dtype == np.float32 and got.shape == (int(n * (sr_new / sr_orig)),)
+    np.testing.assert_array_equal(got, want)
+    got2 = rs.resample(st, sr_orig, sr_new)
+    np.testing.assert_array_equal(got2, resampy_np.resample(st, sr_orig, sr_new))
+    np.testing.assert_array_equal(got2[0], got)
+    assert rs.resample(x, sr_orig, sr_orig) is x  # utils.py:56-57
+
+
+def test_resample_errors_and_coerce_audio_paths(tmp_path):
+    import wave
+
+    from oracle import resampy_np
+    from track_analyser_b200 import io as tio, resample as rs
+    from track_analyser_b200.utils import AudioInput, coerce_audio
+
+    with pytest.raises(ValueError):
+        rs.resample(np.zeros(1, np.float32), 48_000, 8_000)  # resampy: "too small to resample"
+    sr = 22_050  # like the reference's tests/test_cli.py: a 22.05 kHz PCM16 file is brought to 44.1 kHz
+    t = np.arange(sr // 2) / sr
+    pcm = np.round(0.5 * np.sin(2 * np.pi * 220.0 * t) * 32767).astype("<i2")
+    path = tmp_path / "tone.wav"
+    with wave.open(str(path), "wb") as w:
+        w.setnchannels(1); w.setsampwidth(2); w.setframerate(sr); w.writeframes(pcm.tobytes())
+    x = pcm.astype(np.float32) / 32768.0
+    want = resampy_np.resample(x, sr, 44_100)
+    a = coerce_audio(str(path))
+    assert a.sample_rate == 44_100 and a.stereo_samples is None
+    np.testing.assert_array_equal(a.samples, want)
+    data, got_sr, meta = tio.load_audio(str(path), target_sr=44_100, mono=True)
+    assert got_sr == 44_100 and meta["duration"] == pytest.approx(0.5, abs=1e-4)
+    np.testing.assert_array_equal(data, want)
+    b = coerce_audio((x.tolist(), sr))
+    np.testing.assert_array_equal(b.samples, want)
+    st = np.stack([x, -x])
+    c = coerce_audio(AudioInput(samples=x, sample_rate=sr, stereo_samples=st))
+    np.testing.assert_array_equal(c.stereo_samples, resampy_np.resample(st, sr, 44_100))
+    from track_analyser_b200 import pipeline
+
+    res = pipeline.analyse_track(str(path))
+    assert res.audio.sample_rate == 44_100 and len(res.audio.samples) == len(want)

@@ -89,8 +89,11 @@ def test_coerce_audio_shapes():
     assert utils.coerce_audio(a).samples is not None and a.duration == st.shape[1] / 44_100
     with pytest.raises(TypeError):
         utils.coerce_audio(123)
-    with pytest.raises(NotImplementedError):
-        utils.coerce_audio(utils.AudioInput(st[0], 48_000))
+    import torch
+
+    if not torch.cuda.is_available():  # another rate means resampling on the device: no CPU fallback, fail loudly
+        with pytest.raises((RuntimeError, AssertionError)):
+            utils.coerce_audio(utils.AudioInput(st[0], 48_000))
 
 
 def test_wav_reader_round_trip(tmp_path):
@@ -197,3 +200,29 @@ def test_vectorised_chord_estimate_equals_per_template_loop():
         want.append((float(br.beat_times[idx]), names[best], float(scores[best] / float(np.max(scores + 1e-9)))))
     got = [(h.time, h.chord, h.confidence) for h in harmony._estimate_chords(chroma, br, np.random.default_rng(7))]
     assert got == want and len(got) > 250
+
+
+def test_resampy_restatement_properties():
+    """oracle/resampy_np.py is unpinned (resampy is not installed); these are the properties band-limited
+    interpolation must have: output length int(n * ratio), unit DC gain and float32-accurate reconstruction of an
+    in-band tone when up-sampling, stop-band rejection when down-sampling."""
+    from oracle import resampy_np as R
+
+    win, num_table = R.kaiser_best()
+    assert win.shape == (64 * 512 + 1,) and num_table == 512 and win[0] == R.KAISER_BEST["rolloff"]
+    sr0, sr1 = 22_050, 44_100
+    t = np.arange(sr0 // 2) / sr0
+    x = (0.5 * np.sin(2 * np.pi * 1000.0 * t)).astype(np.float32)
+    y = R.resample(x, sr0, sr1)
+    assert y.dtype == np.float32 and y.shape == (int(len(x) * 2.0),)
+    tt = np.arange(len(y)) / sr1
+    assert np.max(np.abs(y - 0.5 * np.sin(2 * np.pi * 1000.0 * tt))[3000:-3000]) < 1e-6
+    dc = R.resample(np.ones(3000, np.float32), sr0, sr1)
+    assert np.max(np.abs(dc[1000:-1000] - 1.0)) < 2e-6
+    assert R.resample(np.ones(48_000, np.float32), 48_000, 44_100).shape == (44_100,)
+    tone = np.sin(2 * np.pi * 23_000.0 * np.arange(24_000) / 48_000).astype(np.float32)  # above the new Nyquist
+    assert np.max(np.abs(R.resample(tone, 48_000, 44_100)[2000:-2000])) < 2e-3
+    st = np.stack([x, -x])
+    np.testing.assert_array_equal(R.resample(st, sr0, sr1)[1], R.resample(-x, sr0, sr1))
+    with pytest.raises(ValueError):
+        R.resample(np.zeros(1, np.float32), 48_000, 8_000)

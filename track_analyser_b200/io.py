@@ -1,7 +1,8 @@
 """Minimal WAV decoding (mirror of ``io.load_audio``'s return contract, io.py:56-139).
 
-Decode/resample is outside the hot path; this reader
-exists so ``analyse_track(path)`` works on PCM16/24/32 and float32 WAV files.
+Container parsing stays on the host; sample conversion has a device
+kernel (``engine.decode_pcm``) and so has resampling (``resample.resample``).  This reader exists so
+``analyse_track(path)`` works on PCM16/24/32 and float32 WAV files.
 Returns ``(samples, sample_rate, metadata)`` with planar ``(channels, N)`` float32
 samples like the reference (io.py:79).
 """
@@ -46,8 +47,12 @@ def load_audio(path: str, target_sr=None, mono: bool = False):
     else:
         raise RuntimeError(f"Could not decode audio file {path}: unsupported WAV format {tag}/{bits}")
     x = x[: (x.size // channels) * channels].reshape(-1, channels).T
-    if target_sr is not None and int(target_sr) != int(sr):
-        raise NotImplementedError("resampling is outside the B200 frontend's scope (SURVEY 8f rank 4)")
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if target_sr is not None and int(target_sr) != int(sr):  # io.py:126-128
+        from .resample import resample
+
+        x = resample(x, int(sr), int(target_sr))
+        sr = int(target_sr)
     samples = np.ascontiguousarray(x[0] if channels == 1 else x, dtype=np.float32)
     if mono and samples.ndim > 1:
         samples = np.mean(samples, axis=0)

@@ -3,9 +3,9 @@
 Same public names and semantics as /root/reference/src/track_analyser/utils.py:
 ``AudioInput`` (:28-39), ``DEFAULT_SR``/``DEFAULT_SEED`` (:24-25),
 ``seed_everything`` (:48-52), ``deterministic_rng`` (:42-45), ``coerce_audio``
-(:73-146).  File decoding and resampling are outside the hot path (SURVEY.md
-section 8f rank 4): WAV files are decoded by ``io.load_audio``; inputs whose
-sample rate differs from ``target_sr`` are rejected instead of being resampled.
+(:73-146).  WAV files are decoded by ``io.load_audio``; inputs whose sample rate
+differs from ``target_sr`` are converted on the device by ``resample.resample``
+(the reference's resampy call, utils.py:55-70).
 """
 
 from __future__ import annotations
@@ -42,12 +42,13 @@ def seed_everything(seed: int = DEFAULT_SEED) -> None:
     random.seed(seed)
 
 
-def _need_same_rate(sr: int, target_sr: int) -> None:
-    if int(sr) != int(target_sr):
-        raise NotImplementedError(
-            f"resampling {sr} -> {target_sr} Hz is outside the B200 frontend's scope (SURVEY 8f rank 4); "
-            "pass an AudioInput at its native rate instead"
-        )
+def _resample(samples: np.ndarray, orig_sr: int, target_sr: int) -> np.ndarray:
+    """utils.py:55-70: resampy.resample per channel, here one device call for all channels."""
+    if orig_sr == target_sr:
+        return samples
+    from .resample import resample
+
+    return resample(samples, orig_sr, target_sr)
 
 
 def _split(samples: np.ndarray, mono: bool):
@@ -58,25 +59,38 @@ def _split(samples: np.ndarray, mono: bool):
 
 
 def coerce_audio(source, *, target_sr: int = DEFAULT_SR, mono: bool = True) -> AudioInput:
-    if isinstance(source, AudioInput):
-        _need_same_rate(source.sample_rate, target_sr)
+    if isinstance(source, AudioInput):  # utils.py:86-101
+        samples = np.asarray(source.samples, dtype=np.float32)
         stereo = None if source.stereo_samples is None else np.asarray(source.stereo_samples, dtype=np.float32)
-        return AudioInput(np.asarray(source.samples, dtype=np.float32), target_sr, source.path, stereo)
-    if isinstance(source, (str, Path)):
+        if source.sample_rate != target_sr:
+            samples = _resample(samples, source.sample_rate, target_sr)
+            if stereo is not None:
+                stereo = _resample(stereo, source.sample_rate, target_sr)
+        return AudioInput(samples, target_sr, source.path, stereo)
+    if isinstance(source, (str, Path)):  # utils.py:103-122
         from .io import load_audio
 
         data, sr, _meta = load_audio(str(source), mono=False)
-        _need_same_rate(sr, target_sr)
         if data.ndim > 1:
             stereo = np.asarray(data, dtype=np.float32)
-            return AudioInput(np.mean(stereo, axis=0), target_sr, str(source), stereo)
-        return AudioInput(np.asarray(data, dtype=np.float32), target_sr, str(source), None)
+            mono_samples = np.mean(stereo, axis=0)
+        else:
+            stereo = None
+            mono_samples = np.asarray(data, dtype=np.float32)
+        mono_samples = _resample(mono_samples, sr, target_sr)
+        if stereo is not None:
+            stereo = _resample(stereo, sr, target_sr)
+            if mono:
+                mono_samples = np.mean(stereo, axis=0)
+        return AudioInput(mono_samples, target_sr, str(source), stereo)
     if isinstance(source, np.ndarray):
         samples, stereo = _split(source, mono)
         return AudioInput(samples, target_sr, None, stereo)
-    if isinstance(source, tuple) and len(source) == 2:
+    if isinstance(source, tuple) and len(source) == 2:  # utils.py:134-144
         data, sr = source
-        _need_same_rate(int(sr), target_sr)
         samples, stereo = _split(np.asarray(list(data), dtype=np.float32), mono)
+        samples = _resample(samples, int(sr), target_sr)
+        if stereo is not None:
+            stereo = _resample(stereo, int(sr), target_sr)
         return AudioInput(samples, target_sr, None, stereo)
     raise TypeError(f"Unsupported audio source type: {type(source)!r}")
