@@ -489,6 +489,49 @@ def test_tempogram_other_window_length():
     np.testing.assert_allclose(r["tempogram"], ref, rtol=RTOL, atol=5e-6)
 
 
+def _standalone_tempogram(plan, env):
+    """ta_tempogram on a caller-supplied envelope (one track of len(env) frames)."""
+    lib = nat.load()
+    T = len(env)
+    batch = engine.upload(plan, [np.zeros((T - 1) * plan.hop, np.float32)])
+    assert int(batch.n_frames[0]) == T
+    d_env = torch.zeros(batch.total_pitch, dtype=torch.float32, device="cuda")
+    d_env[:T] = torch.from_numpy(np.asarray(env, np.float32)).cuda()
+    out = torch.empty(plan.tempogram_win * batch.total_pitch, dtype=torch.float32, device="cuda")
+    ws = engine.workspace(plan, batch)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    nat.check(lib.ta_tempogram(plan._h, C.byref(batch.c_batch), C.c_void_p(d_env.data_ptr()), C.c_void_p(out.data_ptr()),
+                               C.c_void_p(ws.data_ptr()), ws.numel(), stream))
+    torch.cuda.synchronize()
+    return out.cpu().numpy().reshape(plan.tempogram_win, batch.total_pitch)[:, :T]
+
+
+def test_tempogram_sliding_sums_survive_level_jumps_silence_and_negative_values():
+    """The sliding formulation keeps running float64 sums over thousands of frames: a loud passage followed by digital
+    silence must give exact zeros, one followed by a 1e5 times quieter passage must keep full relative accuracy
+    (the block re-derives its sums when the error bound says so), and an envelope with negative values (only
+    reachable through the standalone entry point) takes the path that tracks the L1 norm separately."""
+    sr = 44_100
+    plan = plan_for(sr)
+    rng = np.random.default_rng(5)
+    T = 9000
+    env = np.zeros(T, np.float32)
+    env[:3000] = 8.0 * rng.random(3000).astype(np.float32) * (rng.random(3000) < 0.2)   # loud, sparse onsets
+    env[3000:4500] = 0.0                                                                # digital silence
+    env[4500:6500] = 8e-5 * rng.random(2000).astype(np.float32)                         # 1e5 x quieter
+    env[6500:] = (rng.standard_normal(T - 6500) * 0.5).astype(np.float32)               # signed values
+    got = _standalone_tempogram(plan, env)
+    ref = olr.tempogram(onset_envelope=env, sr=sr, hop_length=512)
+    assert got.shape == ref.shape
+    quiet = slice(3000 + 192, 4500 - 192)  # frames whose whole window is silent
+    assert np.all(got[:, quiet] == 0.0)
+    np.testing.assert_allclose(got, ref, rtol=RTOL, atol=5e-6)
+    # and a long steady envelope: no drift at the far end of a chunk
+    env2 = (1.0 + 0.5 * np.sin(np.arange(20_000) * 0.05)).astype(np.float32)
+    np.testing.assert_allclose(_standalone_tempogram(plan, env2), olr.tempogram(onset_envelope=env2, sr=sr, hop_length=512),
+                               rtol=RTOL, atol=5e-6)
+
+
 def test_tempogram_short_track_inside_window():
     sr = 44_100
     g = np.load(os.path.join(GOLDEN, "tiny_click.npz"))  # T = 175 < 384
