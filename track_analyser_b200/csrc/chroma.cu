@@ -191,6 +191,9 @@ __global__ void __launch_bounds__(256) chroma_fb_kernel(const double* __restrict
 // raw[c, t] = sum_f fb[c, f] * |X[f, t]|^2, then each frame divided by its max: four frames per thread (one
 // 128-bit read of the magnitude row per bin, packed FFMA2 with the filterbank weight as broadcast operand),
 // bins unrolled by four so that four row reads are in flight per thread.
+#ifndef CP_ROWS
+#define CP_ROWS 8  // magnitude rows whose 128-bit loads are in flight per thread
+#endif
 __global__ void __launch_bounds__(128) chroma_project_kernel(const TrackDesc* __restrict__ tracks, const float* __restrict__ mag,
                                                             const float* __restrict__ fb, float* __restrict__ out, int n_bins) {
     using namespace p2;
@@ -224,12 +227,12 @@ __global__ void __launch_bounds__(128) chroma_project_kernel(const TrackDesc* __
         for (int i = threadIdx.x; i < kn * 12; i += blockDim.x) wsm[i] = w[size_t(k0) * 12 + i];
         __syncthreads();
         int kk = 0;
-        for (; kk + 4 <= kn; kk += 4) {
-            float4 m[4];
+        for (; kk + CP_ROWS <= kn; kk += CP_ROWS) {
+            float4 m[CP_ROWS];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) m[u] = __ldg(reinterpret_cast<const float4*>(col + size_t(k0 + kk + u) * td.ld));
+            for (int u = 0; u < CP_ROWS; ++u) m[u] = __ldg(reinterpret_cast<const float4*>(col + size_t(k0 + kk + u) * td.ld));
 #pragma unroll
-            for (int u = 0; u < 4; ++u) accumulate(m[u], wsm + (kk + u) * 12);
+            for (int u = 0; u < CP_ROWS; ++u) accumulate(m[u], wsm + (kk + u) * 12);
         }
         for (; kk < kn; ++kk) accumulate(__ldg(reinterpret_cast<const float4*>(col + size_t(k0 + kk) * td.ld)), wsm + kk * 12);
     }
