@@ -99,3 +99,73 @@ def test_golden_fixtures_match_oracle():
     np.testing.assert_allclose(fe.spectral_centroid_series(x, sr), g["centroid"], rtol=1e-9)
     np.testing.assert_array_equal(fe.spectral_rolloff_series(x, sr), g["rolloff"])
     assert fe.measure_loudness(x, sr)[0] == pytest.approx(float(g["lufs"]), abs=1e-9)
+
+
+def test_chroma_mel_db_and_spectrogram_match_transformers_port():
+    """transformers.audio_utils carries its own port of librosa's filters.chroma / filters.mel / power_to_db / stft
+    framing: an implementation independent of oracle/librosa_np.py with the same specification."""
+    au = pytest.importorskip("transformers.audio_utils")
+    sr, n_fft = 44_100, 2048
+    for tuning in (0.0, 0.23, -0.41):  # the tuning estimate shifts the filterbank (harmony.py:108 -> estimate_tuning)
+        theirs = au.chroma_filter_bank(num_frequency_bins=n_fft, num_chroma=12, sampling_rate=sr, tuning=tuning)
+        np.testing.assert_allclose(lr.filters_chroma(sr, n_fft, tuning=tuning), theirs, rtol=0, atol=1e-7)
+    mel = au.mel_filter_bank(num_frequency_bins=n_fft // 2 + 1, num_mel_filters=128, min_frequency=0.0,
+                             max_frequency=sr / 2, sampling_rate=sr, norm="slaney", mel_scale="slaney")
+    np.testing.assert_allclose(lr.filters_mel(sr, n_fft, 128), mel.T, rtol=0, atol=1e-8)
+    x = np.abs(np.random.default_rng(0).standard_normal((40, 30))) ** 2
+    np.testing.assert_array_equal(lr.power_to_db(x), au.power_to_db(x, reference=1.0, min_value=1e-10, db_range=80.0))
+    y = np.random.default_rng(1).standard_normal(20_000).astype(np.float32)
+    win = au.window_function(n_fft, "hann")
+    np.testing.assert_allclose(lr.get_window("hann", n_fft), win, rtol=0, atol=1e-15)
+    # librosa 0.10 centres with zero padding (pad_mode="constant")
+    spec = au.spectrogram(y, win, frame_length=n_fft, hop_length=512, fft_length=n_fft, power=2.0, center=True,
+                          pad_mode="constant")
+    ours = lr.spectrogram(y, n_fft, 512, 2.0)
+    assert spec.shape == ours.shape and np.max(np.abs(spec - ours)) <= 1e-6 * ours.max()
+    melspec = au.spectrogram(y, win, frame_length=n_fft, hop_length=512, fft_length=n_fft, power=2.0, center=True,
+                             pad_mode="constant", mel_filters=mel)
+    ours = lr.melspectrogram(y, sr, n_fft=n_fft, hop_length=512, n_mels=128)
+    assert np.max(np.abs(melspec - ours)) <= 1e-6 * ours.max()
+
+
+def test_mfcc_and_resampler_match_torchaudio():
+    """MFCC: torchaudio's orthonormal DCT-II matrix.  Resampler: torchaudio's sinc_interp_kaiser with the
+    kaiser_best design (64 zero crossings, roll-off 0.9476, beta 14.7697 -- torchaudio's own default beta is
+    resampy's) is a different realisation of the same filter (exact kernel per phase instead of a 512-per-crossing
+    table with linear interpolation), so the two agree to ~1e-4, not bit for bit."""
+    ta = pytest.importorskip("torchaudio")
+    import torch
+
+    from oracle import resampy_np
+
+    rng = np.random.default_rng(0)
+    S = rng.standard_normal((128, 50))
+    D = ta.functional.create_dct(13, 128, norm="ortho").numpy().T
+    np.testing.assert_allclose(lr.mfcc(S), D @ S, rtol=0, atol=2e-5)  # torchaudio's matrix is float32
+    for sr0, sr1 in ((22_050, 44_100), (48_000, 44_100), (44_100, 48_000)):
+        n = sr0 // 2
+        t = np.arange(n) / sr0
+        x = (0.4 * np.sin(2 * np.pi * 997 * t) + 0.2 * np.sin(2 * np.pi * 5000 * t) + 0.01 * rng.standard_normal(n)).astype(np.float32)
+        ours = resampy_np.resample(x, sr0, sr1)
+        theirs = ta.functional.resample(torch.from_numpy(x), sr0, sr1, lowpass_filter_width=64,
+                                        rolloff=resampy_np.KAISER_BEST["rolloff"], resampling_method="sinc_interp_kaiser",
+                                        beta=resampy_np.KAISER_BEST["beta"]).numpy()
+        assert len(ours) == len(theirs)
+        assert np.max(np.abs(ours - theirs)) < 5e-4
+
+
+def test_tempogram_matches_direct_windowed_autocorrelation():
+    """librosa.feature.tempogram restated (oracle) against the definition: pad by win/2 with a linear ramp, frame,
+    Hann, direct O(win^2) autocorrelation per frame, divide by the frame's largest magnitude."""
+    rng = np.random.default_rng(2)
+    env = np.abs(rng.standard_normal(90)).astype(np.float32)
+    win = 16
+    got = lr.tempogram(onset_envelope=env, sr=22_050, hop_length=512, win_length=win)
+    pad = np.pad(env, (win // 2, win // 2), mode="linear_ramp", end_values=[0, 0]).astype(np.float64)
+    w = scipy.signal.get_window("hann", win, fftbins=True)
+    want = np.zeros((win, len(env)))
+    for t in range(len(env)):
+        z = pad[t:t + win] * w
+        ac = np.array([np.dot(z[: win - l], z[l:]) for l in range(win)])
+        want[:, t] = ac / max(np.max(np.abs(ac)), np.finfo(np.float64).tiny)
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6)
