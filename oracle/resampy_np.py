@@ -8,7 +8,9 @@ reaches it at utils.py:55-70 (``_resample``: one call per channel, default filte
 PARITY UNPINNED: resampy is not installed in this image, the reference holds no golden vectors for its output
 (tests/test_cli.py only checks that a resampled 22.05 kHz file produces reports), and the interpolation window is
 rebuilt here from the filter's published design parameters instead of being read from resampy's packaged
-``kaiser_best.npz``.  What is restated, from the published algorithm (J. O. Smith's band-limited interpolation
+``kaiser_best.npz``.  Sanity pin (tests/test_oracle_crosschecks.py): torchaudio's ``sinc_interp_kaiser`` with the
+same design -- whose default Kaiser beta is this very number -- agrees to < 5e-4; band-limited interpolation
+properties in tests/test_host_logic.py.  What is restated, from the published algorithm (J. O. Smith's band-limited interpolation
 as implemented in resampy 0.4 ``core.resample`` / ``interpn.resample_f``) [UPSTREAM-RECALL]:
 
 * window: ``sinc_window(num_zeros=64, precision=9, rolloff=0.9475937167399596)`` tapered by the right half of a
