@@ -197,8 +197,7 @@ __global__ void __launch_bounds__(256) chroma_fb_kernel(const double* __restrict
 __global__ void __launch_bounds__(128) chroma_project_kernel(const TrackDesc* __restrict__ tracks, const float* __restrict__ mag,
                                                             const float* __restrict__ fb, float* __restrict__ out, int n_bins) {
     using namespace p2;
-    constexpr int KC = 128;
-    __shared__ __align__(16) float wsm[KC * 12];
+    extern __shared__ __align__(16) float wsm[];  // [n_bins * 12]
     const TrackDesc td = tracks[blockIdx.y];
     if (blockIdx.x * blockDim.x * 4 >= td.n_frames) return;
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -221,21 +220,18 @@ __global__ void __launch_bounds__(128) chroma_project_kernel(const TrackDesc* __
             acc[c][1] = pfmas(s1, ww[c], acc[c][1]);
         }
     };
-    for (int k0 = 0; k0 < n_bins; k0 += KC) {
-        const int kn = min(KC, n_bins - k0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < kn * 12; i += blockDim.x) wsm[i] = w[size_t(k0) * 12 + i];
-        __syncthreads();
-        int kk = 0;
-        for (; kk + CP_ROWS <= kn; kk += CP_ROWS) {
-            float4 m[CP_ROWS];
+    // the track's whole filterbank (12 x n_bins floats, 49 KB at n_fft 2048) is staged once: one barrier per CTA
+    for (int i = threadIdx.x; i < n_bins * 12; i += blockDim.x) wsm[i] = w[i];
+    __syncthreads();
+    int kk = 0;
+    for (; kk + CP_ROWS <= n_bins; kk += CP_ROWS) {
+        float4 m[CP_ROWS];
 #pragma unroll
-            for (int u = 0; u < CP_ROWS; ++u) m[u] = __ldg(reinterpret_cast<const float4*>(col + size_t(k0 + kk + u) * td.ld));
+        for (int u = 0; u < CP_ROWS; ++u) m[u] = __ldg(reinterpret_cast<const float4*>(col + size_t(kk + u) * td.ld));
 #pragma unroll
-            for (int u = 0; u < CP_ROWS; ++u) accumulate(m[u], wsm + (kk + u) * 12);
-        }
-        for (; kk < kn; ++kk) accumulate(__ldg(reinterpret_cast<const float4*>(col + size_t(k0 + kk) * td.ld)), wsm + kk * 12);
+        for (int u = 0; u < CP_ROWS; ++u) accumulate(m[u], wsm + (kk + u) * 12);
     }
+    for (; kk < n_bins; ++kk) accumulate(__ldg(reinterpret_cast<const float4*>(col + size_t(kk) * td.ld)), wsm + kk * 12);
     if (!ok) return;
     float res[12][4];
     float mx[4] = {0.f, 0.f, 0.f, 0.f};
@@ -331,7 +327,10 @@ int run_chroma(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_trac
     TA_CUDA(cudaGetLastError());
     TA_REQUIRE((reinterpret_cast<uintptr_t>(mag) & 15) == 0 && (reinterpret_cast<uintptr_t>(chroma) & 15) == 0,
                "magnitude and chroma buffers must be 16-byte aligned");
-    chroma_project_kernel<<<dim3((hb.max_frames + 511) / 512, hb.n_tracks), 128, 0, stream>>>(d_tracks, mag, fb, chroma, plan->n_bins);
+    const size_t fb_smem = size_t(plan->n_bins) * 12 * sizeof(float);
+    TA_CUDA(cudaFuncSetAttribute(chroma_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb_smem));
+    chroma_project_kernel<<<dim3((hb.max_frames + 511) / 512, hb.n_tracks), 128, fb_smem, stream>>>(d_tracks, mag, fb, chroma,
+                                                                                                    plan->n_bins);
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TA_OK;
