@@ -560,34 +560,36 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
     if (rc != TA_OK) return rc;
     auto mark = [&](int i) { if (ev) cudaEventRecord(ev[i], st); };
     mark(0);
-    // The time-domain pass (K5/K6/K8) depends on nothing but the PCM.  Outside the profiled run it is forked onto the
-    // plan's second stream right here, so that its FP64-bound CTAs fill whatever the FFT-bound and HBM-bound kernels of the
-    // main chain leave idle, and joined before returning (the caller's stream sees all results in order).
+    // Two chains are independent of the main one (K1 -> onset -> autocorrelation -> tempogram): the time-domain pass
+    // (K5/K6/K8) depends on nothing but the PCM, and the chroma / HPSS kernels only on K1's magnitude.  Outside the
+    // profiled run both go to the plan's second stream -- the time-domain pass right here, chroma/HPSS after an event
+    // that marks K1's completion -- so that the HBM-bound projection overlaps the FP64-bound tempogram, and are joined
+    // before returning (the caller's stream sees all results in order).  TA_OVERLAP=0: everything on the caller's stream;
+    // TA_OVERLAP=1: only the time-domain pass is forked.
     const bool need_td = out->moments || out->kw_blocks || out->lufs || out->rms_momentary || out->rms_short || out->true_peak;
-    static const bool overlap_enabled = [] { const char* e = std::getenv("TA_OVERLAP"); return !(e && e[0] == '0'); }();
-    const bool fork_td = need_td && !ev && overlap_enabled && plan->aux_stream;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    if (fork_td) {
+    static const int overlap_mode = [] { const char* e = std::getenv("TA_OVERLAP"); return (e && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2; }();
+    const bool fork = !ev && overlap_mode > 0 && plan->aux_stream;
+    const bool fork_td = need_td && fork;
+    const bool fork_mag = fork && overlap_mode > 1;  // chroma / HPSS on the second stream
+    cudaStream_t aux = plan->aux_stream;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_k1 = nullptr;
+    if (fork) {
         TA_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         TA_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        TA_CUDA(cudaEventCreateWithFlags(&ev_k1, cudaEventDisableTiming));
         TA_CUDA(cudaEventRecord(ev_fork, st));
-        TA_CUDA(cudaStreamWaitEvent(plan->aux_stream, ev_fork, 0));
-        rc = run_time_domain(plan, hb, ws, out, plan->aux_stream);
-        cudaEventRecord(ev_join, plan->aux_stream);
-        if (rc != TA_OK) {
-            cudaStreamWaitEvent(st, ev_join, 0);
-            cudaEventDestroy(ev_fork);
-            cudaEventDestroy(ev_join);
-            return rc;
-        }
+        TA_CUDA(cudaStreamWaitEvent(aux, ev_fork, 0));
     }
     auto join = [&]() {
-        if (fork_td) {
+        if (fork) {
+            cudaEventRecord(ev_join, aux);
             cudaStreamWaitEvent(st, ev_join, 0);
             cudaEventDestroy(ev_fork);  // destruction is deferred by the runtime until the events have completed
             cudaEventDestroy(ev_join);
+            cudaEventDestroy(ev_k1);
         }
     };
+    if (fork_td && (rc = run_time_domain(plan, hb, ws, out, aux)) != TA_OK) { join(); return rc; }
     const bool need_flux = out->onset_env || out->flux_linear || out->autocorr || out->tempogram;
     if (need_flux && !out->mel) { join(); set_error("onset/autocorr outputs need the mel output buffer"); return TA_ERR_INVALID; }
     if (out->autocorr && !out->onset_env) { join(); set_error("autocorr output needs the onset_env output buffer"); return TA_ERR_INVALID; }
@@ -601,6 +603,28 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
                            out->frame_max;
     if (need_stft && (rc = run_stft_features(plan, hb, ws, out, st)) != TA_OK) { join(); return rc; }
     mark(1);
+    if ((out->hpss_harmonic || out->hpss_percussive) &&
+        !(out->magnitude && out->hpss_scratch && out->hpss_harmonic && out->hpss_percussive)) {
+        join();
+        set_error("hpss outputs need the magnitude buffer, hpss_scratch and both sum buffers");
+        return TA_ERR_INVALID;
+    }
+    bool chroma_done = false;
+    if (fork_mag && (out->chroma || out->hpss_harmonic)) {  // magnitude consumers on the second stream, behind K1
+        cudaEventRecord(ev_k1, st);
+        cudaStreamWaitEvent(aux, ev_k1, 0);
+        if (out->chroma && (rc = run_chroma(plan, hb, ws.d_tracks, out->magnitude, out->frame_max, out->chroma, out->tuning,
+                                            ws.d_chroma, ws.chroma_bytes, aux)) != TA_OK) {
+            join();
+            return rc;
+        }
+        if (out->hpss_harmonic && (rc = run_hpss(plan, hb, ws.d_tracks, out->magnitude, out->hpss_scratch, out->hpss_harmonic,
+                                                 out->hpss_percussive, aux)) != TA_OK) {
+            join();
+            return rc;
+        }
+        chroma_done = true;
+    }
     if (need_flux && (rc = run_onset_flux(plan, hb, ws.d_tracks, out->mel, ws.d_mel_max, out->onset_env,
                                           out->flux_linear, st)) != TA_OK) {
         join();
@@ -619,22 +643,17 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
     mark(3);
     if (out->tempogram && (rc = run_tempogram(plan, hb, ws.d_tracks, out->onset_env, out->tempogram, st)) != TA_OK) { join(); return rc; }
     mark(4);
-    if (out->chroma && (rc = run_chroma(plan, hb, ws.d_tracks, out->magnitude, out->frame_max, out->chroma, out->tuning,
-                                        ws.d_chroma, ws.chroma_bytes, st)) != TA_OK) {
+    if (out->chroma && !chroma_done &&
+        (rc = run_chroma(plan, hb, ws.d_tracks, out->magnitude, out->frame_max, out->chroma, out->tuning, ws.d_chroma,
+                         ws.chroma_bytes, st)) != TA_OK) {
         join();
         return rc;
     }
-    if (out->hpss_harmonic || out->hpss_percussive) {
-        if (!(out->magnitude && out->hpss_scratch && out->hpss_harmonic && out->hpss_percussive)) {
-            join();
-            set_error("hpss outputs need the magnitude buffer, hpss_scratch and both sum buffers");
-            return TA_ERR_INVALID;
-        }
-        if ((rc = run_hpss(plan, hb, ws.d_tracks, out->magnitude, out->hpss_scratch, out->hpss_harmonic, out->hpss_percussive,
-                           st)) != TA_OK) {
-            join();
-            return rc;
-        }
+    if ((out->hpss_harmonic || out->hpss_percussive) && !chroma_done &&
+        (rc = run_hpss(plan, hb, ws.d_tracks, out->magnitude, out->hpss_scratch, out->hpss_harmonic, out->hpss_percussive,
+                       st)) != TA_OK) {
+        join();
+        return rc;
     }
     mark(5);
     if (need_td && !fork_td && (rc = run_time_domain(plan, hb, ws, out, st)) != TA_OK) return rc;
