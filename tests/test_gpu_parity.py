@@ -626,6 +626,11 @@ def test_mfcc_matches_oracle_and_ragged_batch():
         ref = olr.mfcc(olr.power_to_db(np.asarray(mel, dtype=float) + 1e-9))
         np.testing.assert_allclose(r["mfcc"], ref, rtol=RTOL, atol=5e-3)
     np.testing.assert_allclose(res[2]["mfcc"][1:], 0.0, atol=1e-9)  # silence: flat log-mel, only the DC row is non-zero
+    # another plan shape: 256 mel bands, n_fft 4096, hop 256 (BASELINE configs[4])
+    plan = engine.Plan(sr, 4096, 256, 256, device=0)
+    r = engine.analyse_batch(plan, [a[:, : 2 * sr]], ("mfcc", "mel"))[0]
+    assert r["mfcc"].shape == (13, 1 + 2 * sr // 256)
+    np.testing.assert_allclose(r["mfcc"], olr.mfcc(olr.power_to_db(np.asarray(r["mel"], dtype=float) + 1e-9)), rtol=1e-10, atol=1e-9)
 
 
 def test_hpss_short_track_multiple_reflections():
