@@ -137,7 +137,10 @@ typedef struct ta_frontend_out {
 
 TA_API size_t ta_workspace_bytes(const ta_plan* plan, const ta_batch* batch);
 
-/* Fused schedule K1..K7 for a batch of tracks; see DESIGN.md for the kernels. */
+/* Fused schedule K1..K11 for a batch of tracks; see DESIGN.md for the kernels.  Work is enqueued on `stream`; the
+ * chains that do not depend on the main one (time-domain pass; chroma / HPSS behind K1) run on a second stream owned by
+ * the plan and are joined back into `stream` before the call returns, so the caller sees plain stream ordering
+ * (environment TA_OVERLAP=0 keeps everything on `stream`). */
 TA_API int ta_frontend_run(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out,
                     void* workspace, size_t workspace_bytes, void* stream);
 
