@@ -100,6 +100,7 @@ def main():
         harm, perc = olr.hpss(o["magnitude"])
         rows.append(stats("hpss_harmonic", r["hpss_harmonic"], np.sum(harm, axis=0, dtype=np.float64)))
         rows.append(stats("hpss_percussive", r["hpss_percussive"], np.sum(perc, axis=0, dtype=np.float64)))
+        rows.append(stats("mfcc", r["mfcc"], olr.mfcc(olr.power_to_db(np.asarray(o["mel"], dtype=float) + 1e-9)), atol=5e-3))
         tp_ref = ofe.true_peak_dbtp(mono, args.sr)
         tp_got = 20.0 * np.log10(r["true_peak"] + 1e-12)
         rows.append({"name": "true_peak_db", "got": tp_got, "ref": tp_ref, "abs_err": abs(tp_got - tp_ref)})
