@@ -164,7 +164,7 @@ def test_config4_sixty_minute_48k_track():
     x = np.concatenate([g * base for g in gains], axis=1)
     del base
     assert x.shape == (2, 172_800_000)
-    outs = ("mel", "onset_env", "autocorr", "lufs", "kw_blocks", "moments", "rms_momentary", "ltas")
+    outs = ("mel", "onset_env", "autocorr", "lufs", "kw_blocks", "moments", "rms_momentary", "ltas", "tempogram")
     r = engine.analyse_batch(plan_for(sr), [x], outs)[0]
     assert r.n_frames == 337_501
     mono = np.mean(x, axis=0)
@@ -188,6 +188,14 @@ def test_config4_sixty_minute_48k_track():
     np.testing.assert_allclose(r["onset_env"], env, rtol=RTOL, atol=5e-6)
     ac = olr.autocorrelate(r["onset_env"])
     np.testing.assert_allclose(r["autocorr"], ac, rtol=RTOL, atol=1e-6 * float(ac[0]))
+    # K4b far into the track (frame t only depends on the envelope within 192 frames of t): the sliding sums of a
+    # chunk that starts ~300 000 frames in, and the last frames of the track with their linear-ramp padding
+    for lo, hi in ((300_000, 303_000), (r.n_frames - 2_000, r.n_frames)):
+        a0, a1 = lo - 192, min(hi + 192, r.n_frames)
+        ref = olr.tempogram(onset_envelope=r["onset_env"][a0:a1], sr=sr, hop_length=512)
+        keep = slice(lo - a0, (hi - a0) if a1 < r.n_frames else None)
+        got = r["tempogram"][:, lo:hi if a1 < r.n_frames else r.n_frames]
+        np.testing.assert_allclose(got, ref[:, keep], rtol=RTOL, atol=5e-6)
 
 
 def test_n_fft_1024():
