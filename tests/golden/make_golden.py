@@ -32,6 +32,17 @@ def bundle(x, sr, stereo=None):
         short_db=fe.windowed_loudness(mono, sr, 3.0),
         magnitude_rows=mag[::64].astype(np.float32),  # every 64th bin keeps the fixture small
     )
+    # rows added after the first fixtures: chroma_stft + tuning, tempogram (every 4th frame), HPSS column sums,
+    # MFCC of the structure stage, true peak
+    chroma, tuning = fe.chroma_stft(mono, sr, return_tuning=True)
+    harm, perc = lr.hpss(mag)
+    out.update(
+        chroma=chroma.astype(np.float32), tuning=np.float64(tuning),
+        tempogram_cols=lr.tempogram(onset_envelope=env, sr=sr, hop_length=512)[:, ::4].astype(np.float32),
+        hpss_harmonic=np.sum(harm, axis=0, dtype=np.float64), hpss_percussive=np.sum(perc, axis=0, dtype=np.float64),
+        mfcc=lr.mfcc(lr.power_to_db(np.asarray(mel, dtype=float) + 1e-9)),
+        true_peak_db=np.float64(fe.true_peak_dbtp(mono, sr)),
+    )
     if stereo is not None:
         w = fe.frequency_dependent_width(stereo, sr)
         out.update(stereo=stereo, mid_side_rms=np.array(fe.mid_side_rms(stereo)),

@@ -219,8 +219,25 @@ def test_golden_fixtures():
     np.testing.assert_allclose(r["magnitude"][::64], g["magnitude_rows"], rtol=RTOL, atol=2e-6)
     assert abs(r["lufs"] - float(g["lufs"])) < 0.01
     np.testing.assert_allclose(r["kw_blocks"], g["kw_blocks"], rtol=RTOL, atol=1e-12)
+
+    def widened(res, gold):  # chroma / tuning / tempogram / HPSS sums / MFCC / true peak
+        # frames between the clicks hold nothing but FFT round-off (1e-7 in float32, 1e-16 in the float64 oracle), and
+        # chroma divides each frame by its own maximum: only frames with signal are comparable
+        loud = res["frame_max"] > 1e-3 * float(res["frame_max"].max())
+        assert loud.sum() >= 20
+        np.testing.assert_allclose(res["chroma"][:, loud], gold["chroma"][:, loud], rtol=RTOL, atol=2e-6)
+        assert res["tuning"] == pytest.approx(float(gold["tuning"]), abs=1e-12)
+        np.testing.assert_allclose(res["tempogram"][:, ::4], gold["tempogram_cols"], rtol=RTOL, atol=5e-6)
+        scale = float(np.max(gold["hpss_harmonic"] + gold["hpss_percussive"]))
+        np.testing.assert_allclose(res["hpss_harmonic"], gold["hpss_harmonic"], rtol=RTOL, atol=1e-5 * scale)
+        np.testing.assert_allclose(res["hpss_percussive"], gold["hpss_percussive"], rtol=RTOL, atol=1e-5 * scale)
+        np.testing.assert_allclose(res["mfcc"], gold["mfcc"], rtol=RTOL, atol=5e-3)
+        assert abs(20.0 * np.log10(res["true_peak"] + 1e-12) - float(gold["true_peak_db"])) < 1e-3
+
+    widened(r, g)
     g2 = np.load(os.path.join(GOLDEN, "synth_stereo_4s.npz"))
     r2 = engine.analyse_batch(plan_for(sr), [g2["stereo"]], engine.ALL_OUTPUTS)[0]
+    widened(r2, g2)
     np.testing.assert_allclose(r2["onset_env"], g2["onset_env"], rtol=RTOL, atol=5e-6)
     np.testing.assert_allclose(pstereo.mid_side_from_moments(r2["moments"]), g2["mid_side_rms"], rtol=RTOL)
     freqs = np.fft.rfftfreq(2048, 1.0 / sr)

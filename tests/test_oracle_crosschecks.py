@@ -99,6 +99,18 @@ def test_golden_fixtures_match_oracle():
     np.testing.assert_allclose(fe.spectral_centroid_series(x, sr), g["centroid"], rtol=1e-9)
     np.testing.assert_array_equal(fe.spectral_rolloff_series(x, sr), g["rolloff"])
     assert fe.measure_loudness(x, sr)[0] == pytest.approx(float(g["lufs"]), abs=1e-9)
+    # rows added with the widened scope
+    chroma, tuning = fe.chroma_stft(x, sr, return_tuning=True)
+    np.testing.assert_allclose(chroma, g["chroma"], rtol=1e-6, atol=1e-7)
+    assert tuning == pytest.approx(float(g["tuning"]), abs=1e-12)
+    np.testing.assert_allclose(lr.tempogram(onset_envelope=env, sr=sr, hop_length=512)[:, ::4], g["tempogram_cols"],
+                               rtol=1e-5, atol=1e-6)
+    mag, mel, _, _ = fe.structure_frontend(x, sr)
+    harm, perc = lr.hpss(mag)
+    np.testing.assert_allclose(np.sum(harm, axis=0, dtype=np.float64), g["hpss_harmonic"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(np.sum(perc, axis=0, dtype=np.float64), g["hpss_percussive"], rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(lr.mfcc(lr.power_to_db(np.asarray(mel, dtype=float) + 1e-9)), g["mfcc"], rtol=1e-9, atol=1e-9)
+    assert fe.true_peak_dbtp(x, sr) == pytest.approx(float(g["true_peak_db"]), abs=1e-9)
 
 
 def test_chroma_mel_db_and_spectrogram_match_transformers_port():
