@@ -188,67 +188,61 @@ __global__ void __launch_bounds__(256) chroma_fb_kernel(const double* __restrict
     for (int c = 0; c < 12; ++c) dst[c] = float((w[(c + 3) % 12] / len) * octw);  // roll(-3) then float32
 }
 
-// raw[c, t] = sum_f fb[c, f] * |X[f, t]|^2, then each frame divided by its max: four frames per thread (one
-// 128-bit read of the magnitude row per bin, packed FFMA2 with the filterbank weight as broadcast operand),
-// bins unrolled by four so that four row reads are in flight per thread.
+// raw[c, t] = sum_f fb[c, f] * |X[f, t]|^2, then each frame divided by its max.  Two frames per thread (one 64-bit read of
+// the magnitude row per bin, one packed FFMA2 per chroma bin with the filterbank weight as broadcast operand), eight rows
+// in flight per thread, 256 threads per CTA sharing the track's whole filterbank in shared memory (12 x n_bins floats,
+// 49 KB at n_fft 2048, staged once): ~64 registers, four CTAs = 32 warps per SM.  (The four-frames-per-thread version
+// needed 98 registers: 13 warps per SM, 71 % long-scoreboard stalls at 48 % of the DRAM peak.)
 #ifndef CP_ROWS
-#define CP_ROWS 8  // magnitude rows whose 128-bit loads are in flight per thread
+#define CP_ROWS 8  // magnitude rows whose loads are in flight per thread
 #endif
-__global__ void __launch_bounds__(128) chroma_project_kernel(const TrackDesc* __restrict__ tracks, const float* __restrict__ mag,
-                                                            const float* __restrict__ fb, float* __restrict__ out, int n_bins) {
+static constexpr int CP_THREADS = 256;
+
+__global__ void __launch_bounds__(CP_THREADS, 4) chroma_project_kernel(const TrackDesc* __restrict__ tracks,
+                                                                       const float* __restrict__ mag, const float* __restrict__ fb,
+                                                                       float* __restrict__ out, int n_bins) {
     using namespace p2;
     extern __shared__ __align__(16) float wsm[];  // [n_bins * 12]
     const TrackDesc td = tracks[blockIdx.y];
-    if (blockIdx.x * blockDim.x * 4 >= td.n_frames) return;
-    const int t = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    const bool ok = t < td.n_frames;  // rows are padded to a multiple of 32 frames, so t..t+3 stay inside the row
+    if (blockIdx.x * CP_THREADS * 2 >= td.n_frames) return;
+    const int t = (blockIdx.x * CP_THREADS + threadIdx.x) * 2;
+    const bool ok = t < td.n_frames;  // rows are padded to a multiple of 32 frames, so t, t+1 stay inside the row
     const float* __restrict__ col = mag + size_t(td.pitch_off) * n_bins + (ok ? t : 0);
     const float* __restrict__ w = fb + size_t(blockIdx.y) * n_bins * 12;
-    float2 acc[12][2];
+    float2 acc[12];
 #pragma unroll
-    for (int c = 0; c < 12; ++c) acc[c][0] = acc[c][1] = make_float2(0.f, 0.f);
-    auto accumulate = [&](const float4 m, const float* wk) {
-        const float2 s0 = pmul(make_float2(m.x, m.y), make_float2(m.x, m.y));
-        const float2 s1 = pmul(make_float2(m.z, m.w), make_float2(m.z, m.w));
+    for (int c = 0; c < 12; ++c) acc[c] = make_float2(0.f, 0.f);
+    auto accumulate = [&](const float2 m, const float* wk) {
+        const float2 s = pmul(m, m);
         const float4 w0 = *reinterpret_cast<const float4*>(wk);
         const float4 w1 = *reinterpret_cast<const float4*>(wk + 4);
         const float4 w2 = *reinterpret_cast<const float4*>(wk + 8);
         const float ww[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
 #pragma unroll
-        for (int c = 0; c < 12; ++c) {
-            acc[c][0] = pfmas(s0, ww[c], acc[c][0]);
-            acc[c][1] = pfmas(s1, ww[c], acc[c][1]);
-        }
+        for (int c = 0; c < 12; ++c) acc[c] = pfmas(s, ww[c], acc[c]);
     };
-    // the track's whole filterbank (12 x n_bins floats, 49 KB at n_fft 2048) is staged once: one barrier per CTA
-    for (int i = threadIdx.x; i < n_bins * 12; i += blockDim.x) wsm[i] = w[i];
+    for (int i = threadIdx.x; i < n_bins * 12; i += CP_THREADS) wsm[i] = w[i];
     __syncthreads();
     int kk = 0;
     for (; kk + CP_ROWS <= n_bins; kk += CP_ROWS) {
-        float4 m[CP_ROWS];
+        float2 m[CP_ROWS];
 #pragma unroll
-        for (int u = 0; u < CP_ROWS; ++u) m[u] = __ldg(reinterpret_cast<const float4*>(col + size_t(kk + u) * td.ld));
+        for (int u = 0; u < CP_ROWS; ++u) m[u] = __ldg(reinterpret_cast<const float2*>(col + size_t(kk + u) * td.ld));
 #pragma unroll
         for (int u = 0; u < CP_ROWS; ++u) accumulate(m[u], wsm + (kk + u) * 12);
     }
-    for (; kk < n_bins; ++kk) accumulate(__ldg(reinterpret_cast<const float4*>(col + size_t(kk) * td.ld)), wsm + kk * 12);
+    for (; kk < n_bins; ++kk) accumulate(__ldg(reinterpret_cast<const float2*>(col + size_t(kk) * td.ld)), wsm + kk * 12);
     if (!ok) return;
-    float res[12][4];
-    float mx[4] = {0.f, 0.f, 0.f, 0.f};
+    float2 mx = make_float2(0.f, 0.f);
 #pragma unroll
     for (int c = 0; c < 12; ++c) {
-        res[c][0] = acc[c][0].x; res[c][1] = acc[c][0].y; res[c][2] = acc[c][1].x; res[c][3] = acc[c][1].y;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) mx[q] = fmaxf(mx[q], fabsf(res[c][q]));
+        mx.x = fmaxf(mx.x, fabsf(acc[c].x));
+        mx.y = fmaxf(mx.y, fabsf(acc[c].y));
     }
-    float len[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) len[q] = (mx[q] < 1.1754943508222875e-38f) ? 1.0f : mx[q];
+    const float l0 = (mx.x < 1.1754943508222875e-38f) ? 1.0f : mx.x, l1 = (mx.y < 1.1754943508222875e-38f) ? 1.0f : mx.y;
     float* dst = out + size_t(td.pitch_off) * 12 + t;
 #pragma unroll
-    for (int c = 0; c < 12; ++c)
-        *reinterpret_cast<float4*>(dst + size_t(c) * td.ld) =
-            make_float4(res[c][0] / len[0], res[c][1] / len[1], res[c][2] / len[2], res[c][3] / len[3]);
+    for (int c = 0; c < 12; ++c) *reinterpret_cast<float2*>(dst + size_t(c) * td.ld) = make_float2(acc[c].x / l0, acc[c].y / l1);
 }
 
 // workspace layout helpers ----------------------------------------------------------------
@@ -329,8 +323,8 @@ int run_chroma(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_trac
                "magnitude and chroma buffers must be 16-byte aligned");
     const size_t fb_smem = size_t(plan->n_bins) * 12 * sizeof(float);
     TA_CUDA(cudaFuncSetAttribute(chroma_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb_smem));
-    chroma_project_kernel<<<dim3((hb.max_frames + 511) / 512, hb.n_tracks), 128, fb_smem, stream>>>(d_tracks, mag, fb, chroma,
-                                                                                                    plan->n_bins);
+    chroma_project_kernel<<<dim3((hb.max_frames + 2 * CP_THREADS - 1) / (2 * CP_THREADS), hb.n_tracks), CP_THREADS, fb_smem, stream>>>(
+        d_tracks, mag, fb, chroma, plan->n_bins);
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TA_OK;
