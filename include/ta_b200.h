@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define TA_ABI_VERSION 3
+#define TA_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define TA_API __attribute__((visibility("default")))
@@ -131,8 +131,15 @@ typedef struct ta_frontend_out {
     float* hpss_scratch;   /* [B * P]  caller-provided scratch (time-direction medians); required with the two above */
     double* mfcc;          /* [TA_N_MFCC * P] librosa.feature.mfcc(S=power_to_db(mel + 1e-9), n_mfcc=13), float64:
                               analysis/structure.py:192,199 (needs mel) */
+    float* chroma_cqt;     /* [12 * Pc] librosa.feature.chroma_cqt(y, sr), inf-normalised per frame: harmony.py:107,148.
+                              Pc = sum_i ta_frame_pitch(ta_cqt_frame_count(plan, n_samples[i])); needs magnitude, frame_max,
+                              cqt_tuning and cqt_scratch; plan must be n_fft 2048 / hop 512 (librosa's defaults there) */
+    double* cqt_tuning;    /* [n_tracks] librosa.estimate_tuning(y=y, bins_per_octave=36), the tuning chroma_cqt applies */
+    float* cqt_mag;        /* [252 * Pc] optional: |librosa.cqt(y, sr, n_bins=252, bins_per_octave=36, tuning=cqt_tuning)| */
+    void* cqt_scratch;     /* caller-provided scratch of ta_cqt_scratch_bytes() bytes, 256-byte aligned (decimated signals) */
     int32_t kw_pitch;      /* capacity per track of kw_blocks */
     int32_t rms_pitch;     /* capacity per track of rms_momentary / rms_short */
+    uint64_t cqt_scratch_bytes; /* size of cqt_scratch */
 } ta_frontend_out;
 
 TA_API size_t ta_workspace_bytes(const ta_plan* plan, const ta_batch* batch);
@@ -206,6 +213,18 @@ TA_API int ta_decode_pcm(const void* interleaved, int format, int channels, int6
  * analysis/structure.py:52 as consumed at :143-144 and :212-213.  scratch: B * P floats. */
 TA_API int ta_hpss_curves(const ta_plan* plan, const ta_batch* batch, const float* magnitude, float* scratch,
                           float* harmonic_sum, float* percussive_sum, void* workspace, size_t workspace_bytes, void* stream);
+
+/* K12: librosa.feature.chroma_cqt(y=y, sr=sr) with every default (hop 512, 7 octaves x 36 bins from C1, tuning estimated
+ * from y, norm=inf) on an existing magnitude spectrogram (for the tuning estimate) and the batch's PCM: harmony.py:107,148.
+ * The octave decimator is a stated stage (Kaiser-windowed sinc on soxr HQ's published band edges; librosa calls libsoxr):
+ * DESIGN.md.  Frame count per track: ta_cqt_frame_count (librosa's per-octave STFTs can hold one frame more or less than
+ * 1 + n/hop; the stack is trimmed to the shortest).  ta_cqt_frame_count < 0 / ta_cqt_scratch_bytes == 0: unsupported plan
+ * (text in ta_last_error). */
+TA_API int64_t ta_cqt_frame_count(const ta_plan* plan, int64_t n_samples);
+TA_API size_t ta_cqt_scratch_bytes(const ta_plan* plan, const ta_batch* batch);
+TA_API int ta_chroma_cqt(const ta_plan* plan, const ta_batch* batch, const float* magnitude, const float* frame_max,
+                         float* chroma_cqt, float* cqt_mag, double* cqt_tuning, void* cqt_scratch, size_t cqt_scratch_bytes,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* K4b: windowed (tempogram_win frames, Hann, centred, inf-normalised) autocorrelation of the onset
  * envelope: librosa.feature.tempogram at report.py:260.  Output rows = lags, (win, T_i) per track. */

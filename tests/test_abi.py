@@ -30,10 +30,26 @@ def test_abi_version_and_error_string():
     assert isinstance(lib.ta_last_error(), (bytes, type(None)))
 
 
-def test_struct_layouts_match_header():
-    assert ctypes.sizeof(_native.PlanDesc) == 8 * 4 + 4 * 8
-    assert ctypes.sizeof(_native.Batch) == 8 + 3 * 8
-    assert ctypes.sizeof(_native.FrontendOut) == 23 * 8 + 8
+def test_struct_layouts_match_header(repo_root, tmp_path):
+    """sizeof / offsetof of every ABI struct as gcc sees the header == the ctypes mirror in _native.py."""
+    import subprocess
+
+    structs = {"ta_plan_desc": _native.PlanDesc, "ta_batch": _native.Batch, "ta_frontend_out": _native.FrontendOut}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "ta_b200.h"', "int main(void) {"]
+    for cname, cls in structs.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(repo_root, "include"), "-o", str(exe), str(src)], check=True)
+    got = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == ctypes.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, f"{cname}.{fname}"
 
 
 def test_no_cpu_fallback_without_device():

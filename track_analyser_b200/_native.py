@@ -14,7 +14,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libta_b200.so")
 
-TA_ABI_VERSION = 3
+TA_ABI_VERSION = 4
 TA_OK = 0
 TA_ERR_INVALID = -1
 TA_ERR_CUDA = -2
@@ -83,8 +83,13 @@ class FrontendOut(C.Structure):
         ("hpss_percussive", C.c_void_p),
         ("hpss_scratch", C.c_void_p),
         ("mfcc", C.c_void_p),
+        ("chroma_cqt", C.c_void_p),
+        ("cqt_tuning", C.c_void_p),
+        ("cqt_mag", C.c_void_p),
+        ("cqt_scratch", C.c_void_p),
         ("kw_pitch", C.c_int32),
         ("rms_pitch", C.c_int32),
+        ("cqt_scratch_bytes", C.c_uint64),
     ]
 
 
@@ -104,6 +109,10 @@ SYMBOLS = {
     "ta_onset_flux": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "ta_autocorrelate": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ta_chroma_stft": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ta_cqt_frame_count": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "ta_cqt_scratch_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(Batch)]),
+    "ta_chroma_cqt": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ta_decode_pcm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "ta_hpss_curves": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ta_tempogram": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

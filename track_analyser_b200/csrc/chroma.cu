@@ -30,9 +30,9 @@ struct PeakList {
     const size_t* offset;  // [n_tracks] start of each track's region
 };
 
-__device__ __forceinline__ int residual_bin(float pitch) {
-    // pitch_tuning: residual = mod(12*log2(f/27.5), 1), folded to [-0.5, 0.5); np.histogram over linspace(-0.5,0.5,101)
-    float res = 12.0f * log2f(pitch / 27.5f);
+__device__ __forceinline__ int residual_bin(float pitch, float bpo) {
+    // pitch_tuning: residual = mod(bpo*log2(f/27.5), 1), folded to [-0.5, 0.5); np.histogram over linspace(-0.5,0.5,101)
+    float res = bpo * log2f(pitch / 27.5f);
     res = res - floorf(res);
     if (res >= 0.5f) res -= 1.0f;
     const double x = double(res);
@@ -43,20 +43,23 @@ __device__ __forceinline__ int residual_bin(float pitch) {
     return i;
 }
 
+// POWER: piptrack on |X|^2 (chroma_stft hands estimate_tuning the power spectrogram); otherwise on |X| (estimate_tuning(y=...)
+// as reached from librosa.cqt: _spectrogram(power=1)).  bpo: bins per octave of the tuning residual (12 or 36).
+template <bool POWER>
 __global__ void __launch_bounds__(256) pip_peaks_kernel(const TrackDesc* __restrict__ tracks, const float* __restrict__ mag,
                                                        const float* __restrict__ frame_max, PeakList pl, int n_bins, int kmin,
-                                                       int kmax, float bin_hz) {
+                                                       int kmax, float bin_hz, float bpo) {
     const TrackDesc td = tracks[blockIdx.y];
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= td.n_frames) return;
     const float* __restrict__ col = mag + size_t(td.pitch_off) * n_bins + t;
     const float mx = frame_max[td.pitch_off + t];
-    const float ref = 0.1f * (mx * mx);
+    const float ref = 0.1f * (POWER ? mx * mx : mx);
     float* out_mag = pl.mag + pl.offset[blockIdx.y];
     unsigned char* out_bin = pl.bin + pl.offset[blockIdx.y];
     auto S = [&](int k) {
         const float m = col[size_t(k) * td.ld];
-        return m * m;
+        return POWER ? m * m : m;
     };
     float sm = S(kmin - 1), s0 = S(kmin);
     auto visit = [&](int k, float sp) {
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(256) pip_peaks_kernel(const TrackDesc* __restr
             if (pitch > 0.f) {
                 const unsigned slot = atomicAdd(&pl.count[blockIdx.y], 1u);
                 out_mag[slot] = m;
-                out_bin[slot] = (unsigned char)residual_bin(pitch);
+                out_bin[slot] = (unsigned char)residual_bin(pitch, bpo);
             }
         }
         sm = s0;
@@ -128,7 +131,7 @@ __device__ float block_select(const float* __restrict__ v, unsigned n, unsigned 
     return key_to_float(prefix);
 }
 
-__global__ void __launch_bounds__(1024) tuning_kernel(PeakList pl, double* __restrict__ tuning) {
+__global__ void __launch_bounds__(1024) tuning_kernel(PeakList pl, double* __restrict__ tuning, int* __restrict__ tuning_idx) {
     __shared__ unsigned hist[256];
     __shared__ unsigned bc[2];
     __shared__ unsigned counts[100];
@@ -137,7 +140,10 @@ __global__ void __launch_bounds__(1024) tuning_kernel(PeakList pl, double* __res
     const float* v = pl.mag + pl.offset[trk];
     const unsigned char* b = pl.bin + pl.offset[trk];
     if (n == 0) {  // pitch_tuning on an empty set returns 0.0
-        if (threadIdx.x == 0) tuning[trk] = 0.0;
+        if (threadIdx.x == 0) {
+            tuning[trk] = 0.0;
+            if (tuning_idx) tuning_idx[trk] = 50;
+        }
         return;
     }
     const float lo = block_select(v, n, (n - 1) / 2, hist, bc);
@@ -153,6 +159,7 @@ __global__ void __launch_bounds__(1024) tuning_kernel(PeakList pl, double* __res
         for (int i = 1; i < 100; ++i)
             if (counts[i] > counts[best]) best = i;
         tuning[trk] = -0.5 + best * 0.01;
+        if (tuning_idx) tuning_idx[trk] = best;
     }
 }
 
@@ -259,10 +266,15 @@ static void pip_range(const ta_plan* plan, int& kmin, int& kmax) {
     kmax = std::min(kmax, plan->n_bins - 1);
 }
 
-size_t chroma_scratch_bytes(const ta_plan* plan, const HostBatch& hb) {
+static size_t peaks_per_frame(const ta_plan* plan) {
     int kmin, kmax;
     pip_range(plan, kmin, kmax);
-    const size_t per_frame = size_t(std::max(1, (kmax - kmin + 1) / 2 + 1));
+    return size_t(std::max(1, (kmax - kmin + 1) / 2 + 1));
+}
+
+// scratch of one tuning estimate: peak magnitudes, residual bins, counts, offsets
+size_t tuning_scratch_bytes(const ta_plan* plan, const HostBatch& hb) {
+    const size_t per_frame = peaks_per_frame(plan);
     size_t peaks = 0;
     for (auto& t : hb.tracks) peaks += per_frame * size_t(t.n_frames);
     size_t bytes = 0;
@@ -271,18 +283,21 @@ size_t chroma_scratch_bytes(const ta_plan* plan, const HostBatch& hb) {
     add(peaks);
     add(sizeof(unsigned) * hb.n_tracks);
     add(sizeof(size_t) * hb.n_tracks);
-    add(sizeof(float) * size_t(hb.n_tracks) * plan->n_bins * 12);
     return bytes;
 }
 
-int run_chroma(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_tracks, const float* mag, const float* frame_max,
-               float* chroma, double* tuning, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
-    TA_REQUIRE(plan->desc.n_chroma == 12, "only n_chroma = 12 is implemented");
+size_t chroma_scratch_bytes(const ta_plan* plan, const HostBatch& hb) {
+    return tuning_scratch_bytes(plan, hb) + (sizeof(float) * size_t(hb.n_tracks) * plan->n_bins * 12 + 255) / 256 * 256;
+}
+
+// librosa.estimate_tuning on an existing magnitude spectrogram: piptrack on |X|^2 (power) or |X|, median gate,
+// 0.01-bin histogram of the residuals at `bpo` bins per octave.  tuning_idx (optional): the arg-max histogram bin.
+int run_tuning(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_tracks, const float* mag, const float* frame_max,
+               bool power, int bpo, void* scratch, double* tuning, int* tuning_idx, cudaStream_t stream) {
     TA_REQUIRE(hb.n_tracks <= 65535, "at most 65535 tracks per call");
-    TA_REQUIRE(scratch && scratch_bytes >= chroma_scratch_bytes(plan, hb), "chroma scratch too small");
     int kmin, kmax;
     pip_range(plan, kmin, kmax);
-    const size_t per_frame = size_t(std::max(1, (kmax - kmin + 1) / 2 + 1));
+    const size_t per_frame = peaks_per_frame(plan);
     std::vector<size_t> off(hb.n_tracks);
     size_t peaks = 0;
     for (int i = 0; i < hb.n_tracks; ++i) {
@@ -301,20 +316,30 @@ int run_chroma(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_trac
     pl.bin = take(peaks);
     pl.count = reinterpret_cast<unsigned*>(take(sizeof(unsigned) * hb.n_tracks));
     size_t* d_off = reinterpret_cast<size_t*>(take(sizeof(size_t) * hb.n_tracks));
-    float* fb = reinterpret_cast<float*>(take(sizeof(float) * size_t(hb.n_tracks) * plan->n_bins * 12));
     pl.offset = d_off;
     TA_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(size_t) * hb.n_tracks, cudaMemcpyHostToDevice, stream));
     TA_CUDA(cudaMemsetAsync(pl.count, 0, sizeof(unsigned) * hb.n_tracks, stream));
     const float bin_hz = float(double(plan->desc.sample_rate) / double(plan->desc.n_fft));
     dim3 gf((hb.max_frames + 255) / 256, hb.n_tracks);
     if (kmax > kmin) {
-        pip_peaks_kernel<<<gf, 256, 0, stream>>>(d_tracks, mag, frame_max, pl, plan->n_bins, kmin, kmax, bin_hz);
+        if (power) pip_peaks_kernel<true><<<gf, 256, 0, stream>>>(d_tracks, mag, frame_max, pl, plan->n_bins, kmin, kmax, bin_hz, float(bpo));
+        else pip_peaks_kernel<false><<<gf, 256, 0, stream>>>(d_tracks, mag, frame_max, pl, plan->n_bins, kmin, kmax, bin_hz, float(bpo));
         count_launch();
         TA_CUDA(cudaGetLastError());
     }
-    tuning_kernel<<<hb.n_tracks, 1024, 0, stream>>>(pl, tuning);
+    tuning_kernel<<<hb.n_tracks, 1024, 0, stream>>>(pl, tuning, tuning_idx);
     count_launch();
     TA_CUDA(cudaGetLastError());
+    return TA_OK;
+}
+
+int run_chroma(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_tracks, const float* mag, const float* frame_max,
+               float* chroma, double* tuning, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+    TA_REQUIRE(plan->desc.n_chroma == 12, "only n_chroma = 12 is implemented");
+    TA_REQUIRE(scratch && scratch_bytes >= chroma_scratch_bytes(plan, hb), "chroma scratch too small");
+    int rc = run_tuning(plan, hb, d_tracks, mag, frame_max, true, 12, scratch, tuning, nullptr, stream);
+    if (rc != TA_OK) return rc;
+    float* fb = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + tuning_scratch_bytes(plan, hb));
     chroma_fb_kernel<<<dim3((plan->n_bins + 255) / 256, hb.n_tracks), 256, 0, stream>>>(tuning, fb, plan->n_bins, plan->desc.n_fft,
                                                                                       double(plan->desc.sample_rate));
     count_launch();

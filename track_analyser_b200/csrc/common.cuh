@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -44,6 +45,8 @@ struct Biquad {
     double b0, b1, b2, a1, a2;
 };
 
+struct CqtTables;  // constant-Q tables of a plan (cqt.cu), built on first use
+
 }  // namespace ta
 
 struct ta_plan {
@@ -80,6 +83,9 @@ struct ta_plan {
     int kw_block;   // samples per gating block (0.4 s)
     int kw_step;    // gcd-granule of block bounds
     int rms_m_frame, rms_m_hop, rms_s_frame, rms_s_hop;
+    // constant-Q transform tables (chroma_cqt), built lazily under the mutex by the first call that needs them
+    mutable std::mutex cqt_mutex;
+    mutable ta::CqtTables* cqt = nullptr;
 };
 
 namespace ta {

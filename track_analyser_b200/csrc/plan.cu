@@ -329,6 +329,13 @@ int run_mfcc(const ta_plan*, const HostBatch&, const TrackDesc*, const float* me
 int run_hpss(const ta_plan*, const HostBatch&, const TrackDesc*, const float* mag, float* scratch, float* harm_sum, float* perc_sum,
              cudaStream_t);
 
+int cqt_supported(const ta_plan* plan);
+int64_t cqt_frame_count(const ta_plan* plan, int64_t n_samples);
+size_t cqt_scratch_bytes(const ta_plan* plan, const HostBatch& hb);
+void cqt_tables_free(CqtTables* t);
+int run_chroma_cqt(const ta_plan*, const HostBatch&, const TrackDesc*, const float* mag, const float* frame_max, float* chroma,
+                   float* cqt_mag, double* tuning, void* scratch, size_t scratch_bytes, cudaStream_t);
+
 size_t carve_workspace(const ta_plan* plan, const HostBatch& hb, void* base, Workspace& ws) {
     unsigned char* p = reinterpret_cast<unsigned char*>(base);
     size_t off = 0;
@@ -414,6 +421,7 @@ void ta_plan_destroy(ta_plan* p) {
     cudaFree(p->d_tg_tw1);
     cudaFree(p->d_tg_tw2);
     cudaFree(p->d_tg_window);
+    cqt_tables_free(p->cqt);
     delete p;
 }
 
@@ -548,6 +556,35 @@ int ta_hpss_curves(const ta_plan* plan, const ta_batch* batch, const float* magn
     return run_hpss(plan, hb, ws.d_tracks, magnitude, scratch, harmonic_sum, percussive_sum, st);
 }
 
+int64_t ta_cqt_frame_count(const ta_plan* plan, int64_t n_samples) {
+    if (!plan || n_samples < 0) {
+        set_error("plan must not be NULL and n_samples must be >= 0");
+        return TA_ERR_INVALID;
+    }
+    if (cqt_supported(plan) != TA_OK) return TA_ERR_UNSUPPORTED;
+    return cqt_frame_count(plan, n_samples);
+}
+
+size_t ta_cqt_scratch_bytes(const ta_plan* plan, const ta_batch* batch) {
+    if (!plan || !batch) return 0;
+    HostBatch hb;
+    if (build_host_batch(plan, batch, hb) != TA_OK) return 0;
+    if (cqt_supported(plan) != TA_OK) return 0;
+    return cqt_scratch_bytes(plan, hb);
+}
+
+int ta_chroma_cqt(const ta_plan* plan, const ta_batch* batch, const float* magnitude, const float* frame_max, float* chroma_cqt,
+                  float* cqt_mag, double* cqt_tuning, void* cqt_scratch, size_t cqt_scratch_bytes_, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+    HostBatch hb;
+    Workspace ws;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = prepare(plan, batch, workspace, workspace_bytes, st, hb, ws);
+    if (rc != TA_OK) return rc;
+    return run_chroma_cqt(plan, hb, ws.d_tracks, magnitude, frame_max, chroma_cqt, cqt_mag, cqt_tuning, cqt_scratch,
+                          cqt_scratch_bytes_, st);
+}
+
 uint64_t ta_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out, void* workspace,
@@ -599,6 +636,14 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
         return TA_ERR_INVALID;
     }
     if (out->tempogram && !out->onset_env) { join(); set_error("tempogram output needs the onset_env buffer"); return TA_ERR_INVALID; }
+    if (out->chroma_cqt || out->cqt_mag) {
+        if (!(out->chroma_cqt && out->magnitude && out->frame_max && out->cqt_tuning && out->cqt_scratch)) {
+            join();
+            set_error("chroma_cqt output needs the magnitude, frame_max, cqt_tuning and cqt_scratch buffers");
+            return TA_ERR_INVALID;
+        }
+        if ((rc = cqt_supported(plan)) != TA_OK) { join(); return rc; }
+    }
     const bool need_stft = out->magnitude || out->mel || out->ltas || out->centroid || out->rolloff_bin || out->band_energy ||
                            out->frame_max;
     if (need_stft && (rc = run_stft_features(plan, hb, ws, out, st)) != TA_OK) { join(); return rc; }
@@ -610,7 +655,7 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
         return TA_ERR_INVALID;
     }
     bool chroma_done = false;
-    if (fork_mag && (out->chroma || out->hpss_harmonic)) {  // magnitude consumers on the second stream, behind K1
+    if (fork_mag && (out->chroma || out->hpss_harmonic || out->chroma_cqt)) {  // magnitude consumers on the second stream, behind K1
         cudaEventRecord(ev_k1, st);
         cudaStreamWaitEvent(aux, ev_k1, 0);
         if (out->chroma && (rc = run_chroma(plan, hb, ws.d_tracks, out->magnitude, out->frame_max, out->chroma, out->tuning,
@@ -620,6 +665,12 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
         }
         if (out->hpss_harmonic && (rc = run_hpss(plan, hb, ws.d_tracks, out->magnitude, out->hpss_scratch, out->hpss_harmonic,
                                                  out->hpss_percussive, aux)) != TA_OK) {
+            join();
+            return rc;
+        }
+        if (out->chroma_cqt && (rc = run_chroma_cqt(plan, hb, ws.d_tracks, out->magnitude, out->frame_max, out->chroma_cqt,
+                                                    out->cqt_mag, out->cqt_tuning, out->cqt_scratch,
+                                                    size_t(out->cqt_scratch_bytes), aux)) != TA_OK) {
             join();
             return rc;
         }
@@ -652,6 +703,12 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
     if ((out->hpss_harmonic || out->hpss_percussive) && !chroma_done &&
         (rc = run_hpss(plan, hb, ws.d_tracks, out->magnitude, out->hpss_scratch, out->hpss_harmonic, out->hpss_percussive,
                        st)) != TA_OK) {
+        join();
+        return rc;
+    }
+    if (out->chroma_cqt && !chroma_done &&
+        (rc = run_chroma_cqt(plan, hb, ws.d_tracks, out->magnitude, out->frame_max, out->chroma_cqt, out->cqt_mag,
+                             out->cqt_tuning, out->cqt_scratch, size_t(out->cqt_scratch_bytes), st)) != TA_OK) {
         join();
         return rc;
     }

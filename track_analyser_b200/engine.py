@@ -27,19 +27,22 @@ _TRACE_FETCH = os.environ.get("TA_TRACE_FETCH", "0") not in ("", "0")  # debuggi
 ALL_OUTPUTS = (
     "magnitude", "mel", "onset_env", "autocorr", "flux_linear", "ltas", "centroid", "rolloff_bin",
     "band_energy", "moments", "kw_blocks", "lufs", "rms_momentary", "rms_short", "frame_max", "chroma", "tuning",
-    "tempogram", "true_peak", "hpss_harmonic", "hpss_percussive", "mfcc",
+    "tempogram", "true_peak", "hpss_harmonic", "hpss_percussive", "mfcc", "chroma_cqt", "cqt_tuning", "cqt_mag",
 )
 # SURVEY section 8a (the north-star frontend): what bench.py measures.  true_peak, the HPSS curves and the MFCC are
 # section-8f "next" rows.
-FRONTEND_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o not in ("true_peak", "hpss_harmonic", "hpss_percussive", "mfcc"))
+_NEXT_ROWS = ("true_peak", "hpss_harmonic", "hpss_percussive", "mfcc", "chroma_cqt", "cqt_tuning", "cqt_mag")
+FRONTEND_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o not in _NEXT_ROWS)
 # What the host-side stages of pipeline.analyse_track consume: neither the magnitude (HPSS runs on the device), nor the
 # mel matrix (its only host consumer, the MFCC, runs on the device) nor the plot-only tempogram leave the GPU.
-ANALYSIS_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o not in ("magnitude", "mel", "tempogram"))
-# the bench / default frontend: everything the per-track analysis consumes except the plot-only tempogram
-CORE_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o != "tempogram")
+ANALYSIS_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o not in ("magnitude", "mel", "tempogram", "cqt_mag"))
+# the bench / default frontend: everything the per-track analysis consumes except the plot-only tempogram (and the
+# constant-Q chroma, which only the 2048/512 plan of the harmony stage can produce: ask for it explicitly)
+CORE_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o not in ("tempogram", "chroma_cqt", "cqt_tuning", "cqt_mag"))
 DEFAULT_OUTPUTS = tuple(o for o in CORE_OUTPUTS if o != "magnitude")
 
 
+N_CQT_BINS = 252  # 7 octaves x 36 bins (librosa.feature.chroma_cqt defaults)
 N_MFCC = 13     # TA_N_MFCC
 N_MOMENTS = 10  # TA_N_MOMENTS: sum L, R, L^2, R^2, LR, mid^2, side^2, n, sum |L|, sum |R|
 STAGE_NAMES = ("stft_mel_features", "onset_flux", "autocorrelation", "tempogram", "chroma_stft", "time_domain_loudness")
@@ -128,6 +131,21 @@ class Plan:
             frame += 1
         return frame, max(1, frame // 2)
 
+    @property
+    def cqt_ok(self) -> bool:
+        """Whether this plan can produce the constant-Q outputs (librosa's chroma_cqt defaults: n_fft 2048, hop 512, and a
+        sample rate its basis fits under)."""
+        if getattr(self, "_cqt_ok", None) is None:
+            self._cqt_ok = self.n_fft == 2048 and self.hop == 512 and int(self.lib.ta_cqt_frame_count(self._h, 0)) >= 0
+        return self._cqt_ok
+
+    def cqt_frame_count(self, n_samples: int) -> int:
+        """Frames of librosa.cqt / chroma_cqt for a track of ``n_samples`` (can differ by one from 1 + n // hop)."""
+        n = int(self.lib.ta_cqt_frame_count(self._h, int(n_samples)))
+        if n < 0:
+            nat.check(n)
+        return n
+
     def kw_block_count(self, n_samples: int) -> int:
         T_g = self.meter_block
         if n_samples < T_g * self.sample_rate:
@@ -150,6 +168,14 @@ class DeviceBatch:
         self.c_batch = nat.Batch(self.n_tracks, channels, pcm.data_ptr(),
                                  self.offsets.ctypes.data_as(C.POINTER(C.c_int64)),
                                  self.n_samples.ctypes.data_as(C.POINTER(C.c_int64)))
+
+    def cqt_layout(self):
+        """(frames, pitch, pitch offsets) of the constant-Q outputs (their frame count is librosa's, see ta_cqt_frame_count)."""
+        if getattr(self, "_cqt", None) is None:
+            frames = np.asarray([self.plan.cqt_frame_count(int(n)) for n in self.n_samples], dtype=np.int64)
+            pitch = (frames + 31) & ~31
+            self._cqt = (frames, pitch, np.concatenate([[0], np.cumsum(pitch)]).astype(np.int64))
+        return self._cqt
 
     def rebind(self, plan: Plan) -> "DeviceBatch":
         """The same resident PCM described for another plan (frame counts and pitches follow the plan's hop)."""
@@ -245,6 +271,9 @@ class FrontendBuffers:
             outputs.add("mel")
         if outputs & {"hpss_harmonic", "hpss_percussive"}:
             outputs |= {"hpss_harmonic", "hpss_percussive", "magnitude"}
+        if outputs & {"chroma_cqt", "cqt_tuning", "cqt_mag"}:
+            outputs |= {"chroma_cqt", "cqt_tuning", "magnitude", "frame_max"}
+        Pc = int(batch.cqt_layout()[2][-1]) if "chroma_cqt" in outputs else 0
         max_ns = int(batch.n_samples.max()) if nt else 0
         self.kw_pitch = max(1, plan.kw_block_count(max_ns))
         self.rms_pitch = 1 + max_ns // plan.rms_frames(plan.meter_block)[1]
@@ -260,6 +289,8 @@ class FrontendBuffers:
             "tempogram": ((plan.tempogram_win * P,), torch.float32), "true_peak": ((nt,), torch.float32),
             "hpss_harmonic": ((P,), torch.float32), "hpss_percussive": ((P,), torch.float32),
             "mfcc": ((N_MFCC * P,), torch.float64),
+            "chroma_cqt": ((12 * Pc,), torch.float32), "cqt_tuning": ((nt,), torch.float64),
+            "cqt_mag": ((N_CQT_BINS * Pc,), torch.float32),
         }
         self.t = {k: torch.empty(shapes[k][0], dtype=shapes[k][1], device=dev) for k in ALL_OUTPUTS if k in outputs}
         self.c_out = nat.FrontendOut()
@@ -268,6 +299,15 @@ class FrontendBuffers:
         # device-only scratch of the HPSS kernels (time-direction medians); never copied to the host
         self.hpss_scratch = torch.empty(B * P, dtype=torch.float32, device=dev) if "hpss_harmonic" in outputs else None
         self.c_out.hpss_scratch = self.hpss_scratch.data_ptr() if self.hpss_scratch is not None else None
+        # device-only scratch of the constant-Q chain (decimated signals, peak lists, descriptors)
+        self.cqt_scratch = None
+        if "chroma_cqt" in outputs:
+            need = plan.lib.ta_cqt_scratch_bytes(plan._h, C.byref(batch.c_batch))
+            if need == 0:
+                nat.check(nat.TA_ERR_UNSUPPORTED)
+            self.cqt_scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+            self.c_out.cqt_scratch = self.cqt_scratch.data_ptr()
+            self.c_out.cqt_scratch_bytes = need
         self.c_out.kw_pitch = self.kw_pitch
         self.c_out.rms_pitch = self.rms_pitch
         self.outputs = outputs
@@ -324,7 +364,11 @@ def _cut(plan: Plan, batch: DeviceBatch, i: int, k: str, h: np.ndarray):
         return h[W * po: W * (po + ld)].reshape(W, ld)[:, :T]
     if k == "mfcc":
         return h[N_MFCC * po: N_MFCC * (po + ld)].reshape(N_MFCC, ld)[:, :T]
-    if k in ("tuning", "lufs", "true_peak"):
+    if k in ("chroma_cqt", "cqt_mag"):
+        frames, pitch, off = batch.cqt_layout()
+        rows, Tc, ldc, poc = (12 if k == "chroma_cqt" else N_CQT_BINS), int(frames[i]), int(pitch[i]), int(off[i])
+        return h[rows * poc: rows * (poc + ldc)].reshape(rows, ldc)[:, :Tc]
+    if k in ("tuning", "lufs", "true_peak", "cqt_tuning"):
         return float(h[i])
     if k in ("onset_env", "autocorr", "flux_linear", "centroid", "rolloff_bin", "frame_max", "hpss_harmonic",
              "hpss_percussive"):

@@ -7,12 +7,12 @@ seeded MIDI suggestions are small host-side decisions on (12, T) chroma, restate
 harmony.py:190-465 so that ``analyse_harmony`` / ``key_estimate`` keep the reference's signatures
 and dataclasses.
 
-KNOWN DEVIATION: the reference feeds ``librosa.feature.chroma_cqt`` (harmony.py:107,148) into the key
-scores, chord hints, change points and MIDI suggestions.  chroma_cqt is a multi-rate constant-Q
-transform whose octave down-sampling goes through libsoxr (librosa's default ``res_type``), which
-cannot be restated or pinned here.  ``_chroma_cqt`` below is
-the single place where that kernel plugs in; until then it returns the STFT chroma, so results are
-reference-shaped but not reference-equal wherever chroma_cqt matters.
+``librosa.feature.chroma_cqt`` (harmony.py:107,148) -- the input of the key scores, chord
+hints, change points and MIDI suggestions -- runs on the device too (``csrc/cqt.cu``: tuning estimate,
+2:1 decimation chain, per-octave transforms against the sparsified wavelet basis, chroma fold).  Its octave
+decimator is a STATED stage: librosa calls libsoxr (``soxr_hq``), which is not on this machine; the kernel
+uses a Kaiser-windowed sinc built from soxr HQ's published band edges ("chroma_cqt"), so this
+row is parity-unpinned against the real librosa like the rest of the oracle.
 """
 
 from __future__ import annotations
@@ -191,8 +191,15 @@ def harmony_frontend(audio: AudioInput) -> HarmonyFrontend:
 
 
 def _chroma_cqt(y: np.ndarray, sr: int) -> np.ndarray:
-    """Stand-in for librosa.feature.chroma_cqt (see the module docstring): the STFT chroma."""
-    return chroma_stft(y, sr)[0]
+    """librosa.feature.chroma_cqt(y=y, sr=sr) -> (12, T) float32 (harmony.py:107,148), by the constant-Q kernels of
+    ``csrc/cqt.cu``.  Raises like librosa does when the basis does not fit under the Nyquist frequency."""
+    plan = runtime.get_plan(sr)
+    if not plan.cqt_ok:
+        try:
+            plan.cqt_frame_count(0)
+        except RuntimeError as exc:   # librosa: ParameterError (wavelet basis exceeds the Nyquist frequency)
+            raise ValueError(str(exc)) from exc
+    return runtime.frontend(np.asarray(y, dtype=np.float32), sr, outputs=("chroma_cqt",))["chroma_cqt"]
 
 
 def _beat_profiles(chroma: np.ndarray, beat_result: BeatAnalysis):

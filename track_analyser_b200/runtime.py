@@ -8,6 +8,7 @@ keyed on the sample buffer; outside a session each call runs the kernels afresh.
 
 from __future__ import annotations
 
+import collections
 import contextlib
 import threading
 
@@ -15,8 +16,16 @@ import numpy as np
 
 from . import engine
 
-_plans: dict = {}
+_MAX_PLANS = 16  # least-recently-used plans beyond this are closed (each owns device tables and a workspace)
+_plans: "collections.OrderedDict" = collections.OrderedDict()
+_plans_lock = threading.Lock()
 _local = threading.local()
+
+# What a session computes on the first request for a (buffer, plan): the default 2048/512/128 plan serves ~11 call
+# sites of analyse_track, so it runs everything once; any other plan (e.g. the 4096/1024 one of _spectral_balance)
+# only runs the STFT-feature stage plus what was asked for.
+_LIGHT_OUTPUTS = ("ltas", "centroid", "rolloff_bin", "frame_max", "band_energy")
+_CQT_OUTPUTS = ("chroma_cqt", "cqt_tuning", "cqt_mag")
 
 
 def get_plan(sample_rate: int, n_fft: int = 2048, hop: int = 512, n_mels: int = 128, *, roll_percent: float = 0.85,
@@ -25,18 +34,30 @@ def get_plan(sample_rate: int, n_fft: int = 2048, hop: int = 512, n_mels: int = 
 
     dev = torch.cuda.current_device() if (device is None and torch.cuda.is_available()) else device
     key = (dev, int(sample_rate), int(n_fft), int(hop), int(n_mels), float(roll_percent), float(meter_block))
-    plan = _plans.get(key)
-    if plan is None:
-        plan = engine.Plan(sample_rate, n_fft, hop, n_mels, device=dev, roll_percent=roll_percent,
-                           meter_block=meter_block)
-        _plans[key] = plan
+    with _plans_lock:
+        plan = _plans.get(key)
+        if plan is None:
+            plan = engine.Plan(sample_rate, n_fft, hop, n_mels, device=dev, roll_percent=roll_percent,
+                               meter_block=meter_block)
+            _plans[key] = plan
+            while len(_plans) > _MAX_PLANS:
+                _plans.popitem(last=False)  # dropped here; the plan closes when its last user lets go of it
+        else:
+            _plans.move_to_end(key)
     return plan
 
 
 def _fingerprint(x: np.ndarray):
+    """Identity of a sample buffer inside one session: address, layout and a strided probe of its contents.  The session
+    keeps a reference to every buffer it has fingerprinted (``_pin``), so a temporary cannot be freed and its address
+    reused by different data while the session lives; buffers must not be modified in place inside a session."""
     x = np.asarray(x)
     probe = x.reshape(-1)[:: max(1, x.size // 4096)]
     return (x.__array_interface__["data"][0], x.shape, x.strides, str(x.dtype), hash(probe.tobytes()))
+
+
+def _pin(cache: dict, fp, x: np.ndarray) -> None:
+    cache.setdefault("__pinned__", {})[fp] = x
 
 
 @contextlib.contextmanager
@@ -75,7 +96,20 @@ def alias_mono_to_stereo(mono: np.ndarray, stereo: np.ndarray) -> bool:
             return False
     cache.setdefault("__alias__", {})[_fingerprint(mono)] = _fingerprint(stereo)
     cache.setdefault("__alias_buf__", {})[_fingerprint(stereo)] = stereo
+    _pin(cache, _fingerprint(mono), mono)
     return True
+
+
+def _plan_outputs(plan: engine.Plan, n_mels: int, n_samples: int, outs) -> tuple:
+    """Drop what this plan / track cannot produce from a requested output set."""
+    outs = tuple(outs)
+    if n_samples < plan.meter_block * plan.sample_rate:
+        outs = tuple(o for o in outs if o not in ("kw_blocks", "lufs"))
+    if n_mels == 0:
+        outs = tuple(o for o in outs if o not in ("mel", "onset_env", "autocorr", "flux_linear", "tempogram", "mfcc"))
+    if not plan.cqt_ok:
+        outs = tuple(o for o in outs if o not in _CQT_OUTPUTS)
+    return outs
 
 
 def frontend(samples: np.ndarray, sample_rate: int, *, n_fft: int = 2048, hop: int = 512, n_mels: int = 128,
@@ -86,9 +120,12 @@ def frontend(samples: np.ndarray, sample_rate: int, *, n_fft: int = 2048, hop: i
         x = x[0]
     cache = getattr(_local, "cache", None)
     want = tuple(outputs) if outputs is not None else None
+    plan = get_plan(sample_rate, n_fft, hop, n_mels, roll_percent=roll_percent, meter_block=meter_block)
+    everything = tuple(o for o in engine.ALL_OUTPUTS if o != "cqt_mag")
     key = None
     if cache is not None:
         fp = _fingerprint(x)
+        _pin(cache, fp, x)
         src = None
         if fp in cache.get("__alias__", {}):   # mono view of a stereo buffer that is (or will be) analysed
             src = cache["__alias__"][fp]
@@ -97,16 +134,16 @@ def frontend(samples: np.ndarray, sample_rate: int, *, n_fft: int = 2048, hop: i
         hit = cache.get(key)
         if hit is None and src is not None:
             x = cache["__alias_buf__"][src]   # run on the stereo buffer; the result also serves the mono requests
-        if hit is not None and (want is None or all(o in hit for o in want)):
+        if hit is not None and (want is None or all(o in hit for o in _plan_outputs(plan, n_mels, x.shape[-1], want))):
             return hit
-        want = None  # a session computes everything once
-    plan = get_plan(sample_rate, n_fft, hop, n_mels, roll_percent=roll_percent, meter_block=meter_block)
-    outs = engine.ALL_OUTPUTS if want is None else want
-    if x.shape[-1] < meter_block * sample_rate:
-        outs = tuple(o for o in outs if o not in ("kw_blocks", "lufs"))
-    if want is None:  # "everything" means everything this plan can produce
-        if n_mels == 0:
-            outs = tuple(o for o in outs if o not in ("mel", "onset_env", "autocorr", "flux_linear", "tempogram", "mfcc"))
+        default_plan = (n_fft, hop, n_mels) == (2048, 512, 128)
+        if want is None or default_plan or hit is not None:
+            outs = everything + (tuple(want) if want else ())   # one run serves every later request of the session
+        else:
+            outs = tuple(dict.fromkeys(_LIGHT_OUTPUTS + want))
+    else:
+        outs = everything if want is None else want
+    outs = _plan_outputs(plan, n_mels, x.shape[-1], outs)
     resident = None
     if cache is not None:  # the PCM of this buffer may already be in HBM for another plan of the same session
         pcm_key = ("__pcm__", _fingerprint(x), plan.device)
