@@ -107,9 +107,29 @@ def test_wav_reader_round_trip(tmp_path):
         data = x.tobytes()
         fh.write(b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVEfmt " +
                  struct.pack("<IHHIIHH", 16, 1, 2, 44_100, 44_100 * 4, 4, 16) + b"data" + struct.pack("<I", len(data)) + data)
-    s, sr, meta = tio.load_audio(str(p))
+    s, sr, meta = tio.load_audio(str(p), mono=False)
     assert sr == 44_100 and s.shape == (2, 1000) and meta["channels"] == 2
     np.testing.assert_array_equal(s, (x.astype(np.float32) / 32768.0).T)
+    m, _, _ = tio.load_audio(str(p))  # the reference's default is mono=True: 1-d channel mean (io.py:59,129-138)
+    np.testing.assert_array_equal(m, np.mean(s, axis=0))
+    # WAVE_FORMAT_EXTENSIBLE carrying IEEE float: the SubFormat GUID decides, not the width
+    f = np.random.default_rng(1).uniform(-0.5, 0.5, size=(100, 2)).astype("<f4")
+    guid = struct.pack("<H", 3) + bytes.fromhex("000000001000800000aa00389b71")
+    fmt = struct.pack("<HHIIHH", 0xFFFE, 2, 48_000, 48_000 * 8, 8, 32) + struct.pack("<HHI", 22, 32, 3) + guid
+    with open(p, "wb") as fh:
+        fh.write(b"RIFF" + struct.pack("<I", 20 + len(fmt) + f.nbytes) + b"WAVEfmt " + struct.pack("<I", len(fmt)) + fmt +
+                 b"data" + struct.pack("<I", f.nbytes) + f.tobytes())
+    s, sr, _ = tio.load_audio(str(p), mono=False)
+    assert sr == 48_000
+    np.testing.assert_array_equal(s, f.T)
+    # a mono file keeps the (1, N) shape under mono=False; a 24-bit data chunk with a ragged tail is cut to whole frames
+    raw = bytes(range(1, 3 * 7 + 2 + 1))
+    with open(p, "wb") as fh:
+        fh.write(b"RIFF" + struct.pack("<I", 36 + len(raw) + 1) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, 1, 8_000, 24_000, 3, 24) +
+                 b"data" + struct.pack("<I", len(raw)) + raw + b"\x00")
+    s, sr, meta = tio.load_audio(str(p), mono=False)
+    assert s.shape == (1, 7) and meta["channels"] == 1
+    assert s[0, 0] == np.float32((1 | (2 << 8) | (3 << 16)) / 8388608.0)
 
 
 def test_structure_host_logic_on_oracle_curves_like_reference_test():

@@ -50,7 +50,7 @@ def main():
     x = synth.synth_track(synth.DEFAULT_SEED, 180.0, 44_100, 2)
     ms = timed(plan, resident(plan, x, 1), engine.FRONTEND_OUTPUTS, 10)
     out.append({"config": 1, "what": "one 3-min 44.1 kHz stereo track, full frontend", "ms": ms, "xrt": 180.0 / (ms * 1e-3)})
-    ms = timed(plan, resident(plan, x, 1), engine.ALL_OUTPUTS, 10)
+    ms = timed(plan, resident(plan, x, 1), engine.available_outputs(plan, engine.CORE_OUTPUTS + ('tempogram',)), 10)
     out.append({"config": 1, "what": "same + true peak + HPSS curves", "ms": ms, "xrt": 180.0 / (ms * 1e-3)})
     # configs[3]: one 60-minute 48 kHz stereo track
     plan48 = engine.Plan(48_000, 2048, 512, 128, device=0)

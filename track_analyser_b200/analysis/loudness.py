@@ -75,11 +75,8 @@ def analyse_loudness(audio: AudioInput | str, *, seed: int, meter_block_size: fl
         res = _td(samples, audio.sample_rate, meter_block_size, ("moments",))
         m = res["moments"]
         peak_db = true_peak_dbtp(samples, audio.sample_rate)
-    # sum of mono^2: moments[2] of a mono run, moments[5] (mid^2) when the request was served by the stereo run
-    sq = m[5] if res.channels == 2 else m[2]
-    rms_val = float(np.sqrt(sq / m[7])) if m[7] else 0.0
     return LoudnessAnalysis(
         integrated_lufs=integrated, short_term_lufs=short_term, momentary_lufs=momentary, loudness_range=lra,
         true_peak_dbfs=peak_db,
-        rms_dbfs=float(20.0 * np.log10(rms_val + 1e-12)),
+        rms_dbfs=loudness_host.rms_dbfs_from_moments(m, res.channels == 2),
     )

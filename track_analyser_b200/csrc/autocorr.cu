@@ -206,13 +206,10 @@ int run_autocorrelate(const ta_plan* plan, const HostBatch& hb, const TrackDesc*
     double2* d_work = reinterpret_cast<double2*>(scratch);
     TA_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(size_t) * hb.n_tracks, cudaMemcpyHostToDevice, stream));
     const size_t smem = sizeof(double2) * AC_SMEM_ELEMS;
-    static bool configured = false;
-    if (!configured) {
-        TA_CUDA(cudaFuncSetAttribute(ac_columns_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TA_CUDA(cudaFuncSetAttribute(ac_columns_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        TA_CUDA(cudaFuncSetAttribute(ac_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    // the attribute is per device and plans may live on several devices of one process: set it on every call
+    TA_CUDA(cudaFuncSetAttribute(ac_columns_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TA_CUDA(cudaFuncSetAttribute(ac_columns_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TA_CUDA(cudaFuncSetAttribute(ac_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (max_n1 > 1) {
         ac_columns_kernel<false><<<dim3(max_cols_grid, hb.n_tracks), AC_THREADS, smem, stream>>>(d_tracks, env, d_work, d_off, out);
         count_launch();

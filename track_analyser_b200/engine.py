@@ -48,6 +48,17 @@ N_MOMENTS = 10  # TA_N_MOMENTS: sum L, R, L^2, R^2, LR, mid^2, side^2, n, sum |L
 STAGE_NAMES = ("stft_mel_features", "onset_flux", "autocorrelation", "tempogram", "chroma_stft", "time_domain_loudness")
 
 
+def available_outputs(plan: "Plan", outputs: Iterable[str] = ALL_OUTPUTS) -> tuple:
+    """``outputs`` without what ``plan`` cannot produce: the mel-derived ones when it has no mel bands, the constant-Q
+    ones unless it is librosa's chroma_cqt configuration (n_fft 2048, hop 512, basis below the Nyquist frequency)."""
+    drop = set()
+    if plan.n_mels == 0:
+        drop |= {"mel", "onset_env", "autocorr", "flux_linear", "tempogram", "mfcc"}
+    if not plan.cqt_ok:
+        drop |= {"chroma_cqt", "cqt_tuning", "cqt_mag"}
+    return tuple(o for o in outputs if o not in drop)
+
+
 def frame_count(n_samples: int, hop: int) -> int:
     return 1 + n_samples // hop
 

@@ -130,8 +130,9 @@ def _stereo_image(audio: AudioInput) -> StereoImage:
     m = runtime.frontend(np.ascontiguousarray(samples[:2]), audio.sample_rate, outputs=("moments",))["moments"]
     n = float(m[7])
     cov = m[4] - m[0] * m[1] / n
-    var_l, var_r = m[2] - m[0] * m[0] / n, m[3] - m[1] * m[1] / n
-    denom = np.sqrt(var_l * var_r)
+    # one-pass moments can come out slightly negative for a (near-)constant channel: clamp, the ratio is nan then anyway
+    var_l, var_r = max(m[2] - m[0] * m[0] / n, 0.0), max(m[3] - m[1] * m[1] / n, 0.0)
+    denom = np.sqrt(var_l) * np.sqrt(var_r)
     corr = float(cov / denom) if denom > 0 else float("nan")  # np.corrcoef of a constant channel is nan as well
     return StereoImage(correlation=corr, balance=float(m[8] / n - m[9] / n))
 

@@ -3,8 +3,10 @@
 Container parsing stays on the host; sample conversion has a device
 kernel (``engine.decode_pcm``) and so has resampling (``resample.resample``).  This reader exists so
 ``analyse_track(path)`` works on PCM16/24/32 and float32 WAV files.
-Returns ``(samples, sample_rate, metadata)`` with planar ``(channels, N)`` float32
-samples like the reference (io.py:79).
+Returns ``(samples, sample_rate, metadata)`` like the reference (io.py:56-139): with ``mono=True`` (the
+default) a 1-d float32 array (the channel mean), with ``mono=False`` always planar ``(channels, N)`` --
+``(1, N)`` for a mono file, which is what makes ``coerce_audio`` attach ``stereo_samples`` of shape
+``(1, N)`` to mono files (utils.py:106-108).
 """
 
 from __future__ import annotations
@@ -14,7 +16,7 @@ import struct
 import numpy as np
 
 
-def load_audio(path: str, target_sr=None, mono: bool = False):
+def load_audio(path: str, target_sr=None, mono: bool = True):
     with open(path, "rb") as fh:
         raw = fh.read()
     if raw[:4] != b"RIFF" or raw[8:12] != b"WAVE":
@@ -25,14 +27,21 @@ def load_audio(path: str, target_sr=None, mono: bool = False):
         body = raw[pos + 8:pos + 8 + size]
         if cid == b"fmt ":
             fmt = struct.unpack("<HHIIHH", body[:16])
+            fmt_body = body
         elif cid == b"data":
             data = body
         pos += 8 + size + (size & 1)
     if fmt is None or data is None:
         raise RuntimeError(f"Could not decode audio file {path}: missing fmt/data chunk")
     tag, channels, sr, _, _, bits = fmt
-    if tag == 0xFFFE:  # WAVE_FORMAT_EXTENSIBLE: PCM or float by width
-        tag = 3 if bits == 32 and False else 1
+    if tag == 0xFFFE:  # WAVE_FORMAT_EXTENSIBLE: the first two bytes of the SubFormat GUID are the real format tag
+        if len(fmt_body) < 26:
+            raise RuntimeError(f"Could not decode audio file {path}: truncated WAVE_FORMAT_EXTENSIBLE header")
+        tag = struct.unpack("<H", fmt_body[24:26])[0]
+    if channels < 1:
+        raise RuntimeError(f"Could not decode audio file {path}: no channels")
+    width = bits // 8
+    data = data[: (len(data) // (width * channels)) * width * channels] if width else data  # whole frames only
     if tag == 1 and bits == 16:
         x = np.frombuffer(data, dtype="<i2").astype(np.float32) / 32768.0
     elif tag == 1 and bits == 24:
@@ -53,9 +62,10 @@ def load_audio(path: str, target_sr=None, mono: bool = False):
 
         x = resample(x, int(sr), int(target_sr))
         sr = int(target_sr)
-    samples = np.ascontiguousarray(x[0] if channels == 1 else x, dtype=np.float32)
-    if mono and samples.ndim > 1:
-        samples = np.mean(samples, axis=0)
+    if mono:  # io.py:129-138: mean over channels, squeezed to 1-d
+        samples = np.ascontiguousarray(x[0] if channels == 1 else np.mean(x, axis=0), dtype=np.float32)
+    else:
+        samples = x
     meta = {"path": path, "sample_rate": int(sr), "channels": int(channels), "frames": int(x.shape[1]),
             "duration": float(x.shape[1]) / float(sr)}
     return samples, int(sr), meta
