@@ -16,8 +16,9 @@
  *     allocates or frees caller-visible memory; scratch is the caller-provided
  *     workspace (ta_workspace_bytes).  Plan tables are owned by the plan.
  *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work
- *     on it and returns.  `*_host` entry points take HOST buffers, do the copies
- *     themselves and synchronise the stream before returning.
+ *     on it and returns.  The one exception is ta_frontend_run_host, which takes
+ *     HOST buffers, does the copies itself and synchronises the stream before
+ *     returning (for callers that own no device memory, e.g. a numpy-only binding).
  *   - ragged batches: track i has n_samples[i] samples per channel and
  *     T_i = 1 + n_samples[i] / hop frames.  All (rows, T_i) matrices of track i
  *     are row-major with row pitch ld_i = ta_frame_pitch(T_i) (T_i rounded up to
@@ -67,8 +68,8 @@ TA_API const char* ta_last_error(void);
 typedef struct ta_plan_desc {
     int32_t device;        /* CUDA device ordinal */
     int32_t sample_rate;   /* Hz */
-    int32_t n_fft;         /* 1024, 2048 or 4096 */
-    int32_t hop;           /* hop length in samples, multiple of 4 */
+    int32_t n_fft;         /* 256, 512, 1024, 2048 or 4096 (256 / 512 run zero-padded on the 1024-point transform) */
+    int32_t hop;           /* hop length in samples, any positive value (hop = n_fft/4 takes the shared-sample fast path) */
     int32_t n_mels;        /* mel bands (0: no mel tables) */
     int32_t n_chroma;      /* chroma bins (12) */
     int32_t tempogram_win; /* tempogram window in frames (384) */
@@ -81,6 +82,10 @@ typedef struct ta_plan_desc {
 } ta_plan_desc;
 
 TA_API int ta_plan_create(const ta_plan_desc* desc, ta_plan** out);
+/* Same with an analysis window other than Hann: `window` = n_fft float64 values on the HOST, what
+ * scipy.signal.get_window(name, n_fft, fftbins=True) returns for librosa.stft(window=name) (features.py:66-79 passes
+ * its `window` argument through); NULL = periodic Hann. */
+TA_API int ta_plan_create_window(const ta_plan_desc* desc, const double* window, ta_plan** out);
 TA_API void ta_plan_destroy(ta_plan* plan);
 TA_API int ta_plan_n_bins(const ta_plan* plan);
 
@@ -140,6 +145,8 @@ typedef struct ta_frontend_out {
     int32_t kw_pitch;      /* capacity per track of kw_blocks */
     int32_t rms_pitch;     /* capacity per track of rms_momentary / rms_short */
     uint64_t cqt_scratch_bytes; /* size of cqt_scratch */
+    int32_t true_peak_oversample; /* oversampling factor of true_peak, 1 .. 32; 0 = the reference's default 8 (loudness.py:81) */
+    int32_t reserved;      /* must be 0 */
 } ta_frontend_out;
 
 TA_API size_t ta_workspace_bytes(const ta_plan* plan, const ta_batch* batch);
@@ -150,6 +157,13 @@ TA_API size_t ta_workspace_bytes(const ta_plan* plan, const ta_batch* batch);
  * (environment TA_OVERLAP=0 keeps everything on `stream`). */
 TA_API int ta_frontend_run(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out,
                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ta_frontend_run for callers without device memory: every data pointer of `batch` (pcm) and `out` is a HOST pointer
+ * (pageable or pinned) with the element counts documented on ta_frontend_out; hpss_scratch / cqt_scratch are ignored.
+ * The library takes device memory for the PCM, the requested outputs (and the intermediates they depend on), scratch and
+ * workspace from the stream-ordered pool (cudaMallocAsync), copies in, runs the fused schedule, copies the outputs back,
+ * frees, and synchronises `stream` before returning.  kw_pitch / rms_pitch as for ta_frontend_run. */
+TA_API int ta_frontend_run_host(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out, void* stream);
 
 /* Same schedule as ta_frontend_run, but brackets each stage with CUDA events on
  * `stream`, synchronises, and returns the device time of each stage in

@@ -90,6 +90,8 @@ class FrontendOut(C.Structure):
         ("kw_pitch", C.c_int32),
         ("rms_pitch", C.c_int32),
         ("cqt_scratch_bytes", C.c_uint64),
+        ("true_peak_oversample", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -98,11 +100,13 @@ SYMBOLS = {
     "ta_abi_version": (C.c_int, []),
     "ta_last_error": (C.c_char_p, []),
     "ta_plan_create": (C.c_int, [C.POINTER(PlanDesc), C.POINTER(C.c_void_p)]),
+    "ta_plan_create_window": (C.c_int, [C.POINTER(PlanDesc), C.POINTER(C.c_double), C.POINTER(C.c_void_p)]),
     "ta_plan_destroy": (None, [C.c_void_p]),
     "ta_plan_n_bins": (C.c_int, [C.c_void_p]),
     "ta_plan_table": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t]),
     "ta_workspace_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(Batch)]),
     "ta_frontend_run": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(FrontendOut), C.c_void_p, C.c_size_t, C.c_void_p]),
+    "ta_frontend_run_host": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(FrontendOut), C.c_void_p]),
     "ta_frontend_run_profiled": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(FrontendOut), C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_float)]),
     "ta_launch_count": (C.c_uint64, []),
     "ta_stft_features": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.POINTER(FrontendOut), C.c_void_p, C.c_size_t, C.c_void_p]),

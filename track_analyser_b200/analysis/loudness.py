@@ -14,7 +14,7 @@ from typing import List, Tuple
 
 import numpy as np
 
-from .. import loudness_host, runtime
+from .. import engine, loudness_host, runtime
 from ..utils import AudioInput, seed_everything
 
 
@@ -59,9 +59,15 @@ def true_peak_dbtp(samples: np.ndarray, sample_rate: int, *, oversample: int = 8
     samples = np.asarray(samples, dtype=np.float32)
     if samples.ndim != 1:
         raise ValueError("true_peak_dbtp expects mono audio samples")
-    if oversample != 8:
-        raise NotImplementedError("the device kernel implements the reference's default oversample=8 only")
-    peak = _td(samples, sample_rate, 0.4, ("true_peak",))["true_peak"] if samples.size else 0.0
+    if oversample > 32:
+        raise ValueError("the device kernel oversamples by at most 32")
+    if not samples.size:
+        peak = 0.0
+    elif oversample == 8:
+        peak = _td(samples, sample_rate, 0.4, ("true_peak",))["true_peak"]
+    else:  # not the factor the session's shared run uses: its own pass
+        plan = runtime.get_plan(sample_rate)
+        peak = engine.analyse_batch(plan, [samples], ("true_peak",), true_peak_oversample=int(oversample))[0]["true_peak"]
     return float(20.0 * np.log10(float(peak) + 1e-12))
 
 

@@ -118,5 +118,6 @@ struct Workspace {
     unsigned char* end;
 };
 int stft_tile_frames(int n_fft);
+int stft_transform_length(int n_fft);  // 1024 for n_fft 256 / 512 (zero-padded), else n_fft
 size_t carve_workspace(const ta_plan* plan, const HostBatch& hb, void* base, Workspace& ws);
 }  // namespace ta

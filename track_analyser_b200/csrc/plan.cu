@@ -31,6 +31,7 @@ int run_autocorrelate(const ta_plan*, const HostBatch&, const TrackDesc*, const 
 size_t autocorr_scratch_elems(const HostBatch&);
 int run_time_domain(const ta_plan*, const HostBatch&, const Workspace&, const ta_frontend_out*, cudaStream_t);
 int time_chunk_samples(const ta_plan*, int64_t total_samples);
+void true_peak_design(int up, float* coef, float& gain, float& floor_);
 
 // ---------------------------------------------------------------------------
 // Slaney mel scale exactly as librosa.filters.mel(htk=False, norm="slaney")
@@ -110,15 +111,17 @@ static int upload(T** dptr, const std::vector<T>& h) {
     return TA_OK;
 }
 
-static int plan_build(ta_plan* p) {
+static int plan_build(ta_plan* p, const double* user_window) {
     const ta_plan_desc& d = p->desc;
-    const int N = d.n_fft, M = N / 16, Q = N / 256;
+    const int NF = d.n_fft;                      // the plan's n_fft: window length, bins
+    const int N = stft_transform_length(NF);    // length of the transform that evaluates it (NF zero-padded when NF < 1024)
+    const int M = N / 16, Q = N / 256;
     const double PI = 3.14159265358979323846;
     TA_CUDA(cudaSetDevice(d.device));
     cudaDeviceProp prop;
     TA_CUDA(cudaGetDeviceProperties(&prop, d.device));
     p->sm_count = prop.multiProcessorCount;
-    p->n_bins = N / 2 + 1;
+    p->n_bins = NF / 2 + 1;
 
     // twiddles, exact to float rounding (angle reduced with integer arithmetic first)
     std::vector<float2> tw1(size_t(15) * M), tw2(size_t(16) * Q);
@@ -133,13 +136,14 @@ static int plan_build(ta_plan* p) {
             tw2[size_t(k2) * Q + n3] = make_float2(float(std::cos(a)), float(std::sin(a)));
         }
     // periodic Hann, scipy.signal.get_window("hann", N, fftbins=True): 0.5 - 0.5 cos(2 pi n / N)
-    p->h_window.resize(N);
-    for (int n = 0; n < N; ++n) p->h_window[n] = float(0.5 - 0.5 * std::cos(2.0 * PI * n / N));
+    p->h_window.assign(N, 0.f);                  // zero beyond the frame when the transform is longer than it
+    for (int n = 0; n < NF; ++n)
+        p->h_window[n] = user_window ? float(user_window[n]) : float(0.5 - 0.5 * std::cos(2.0 * PI * n / NF));
     // numpy.fft.rfftfreq(n, d=1/sr): arange(n//2+1) * (1.0 / (n * d))
     p->h_freqs.resize(p->n_bins);
     {
         const double dd = 1.0 / double(d.sample_rate);
-        const double val = 1.0 / (double(N) * dd);
+        const double val = 1.0 / (double(NF) * dd);
         for (int k = 0; k < p->n_bins; ++k) p->h_freqs[k] = double(k) * val;
     }
     int rc;
@@ -204,44 +208,7 @@ static int plan_build(ta_plan* p) {
     double coefs[12];
     biquad_kweight(d.sample_rate, p->shelf, p->highpass, coefs);
 
-    {   // true-peak interpolator: scipy.signal.resample_poly(x, 8, 1) = firwin(161, 1/8, window=("kaiser", 5.0)),
-        // cast to float32 (scipy matches the dtype of x) and scaled by 8; y[8q + ph] = sum_i c[ph][i + 10] * x[q - i]
-        auto bessel_i0 = [](double x) {
-            double s = 1.0, t = 1.0;
-            for (int k = 1; k < 200; ++k) {
-                t *= (x * 0.5) * (x * 0.5) / (double(k) * double(k));
-                s += t;
-                if (t < 1e-18 * s) break;
-            }
-            return s;
-        };
-        const int NT = 161, HL = 80;
-        const double fc = 0.125, beta = 5.0;
-        double h[NT], sum = 0.0;
-        for (int n = 0; n < NT; ++n) {
-            const double m = double(n - HL);
-            const double sinc = (m == 0.0) ? 1.0 : std::sin(PI * fc * m) / (PI * fc * m);
-            const double r = m / double(HL);
-            h[n] = fc * sinc * bessel_i0(beta * std::sqrt(std::max(0.0, 1.0 - r * r))) / bessel_i0(beta);
-            sum += h[n];
-        }
-        float gain = 0.f;
-        for (int ph = 0; ph < 8; ++ph) {
-            float g = 0.f;
-            for (int i = -10; i <= 10; ++i) {
-                const int idx = HL + ph + 8 * i;
-                const float c = (idx >= 0 && idx < NT) ? float(h[idx] / sum) * 8.0f : 0.f;
-                p->tp_coef[ph * 21 + (i + 10)] = c;
-                g += std::fabs(c);
-            }
-            gain = std::max(gain, g);
-        }
-        float others = 0.f;
-        for (int i = -10; i <= 10; ++i)
-            if (i != 0) others += std::fabs(p->tp_coef[i + 10]);
-        p->tp_gain = gain * 1.0001f;                                          // margins cover float32 accumulation
-        p->tp_floor = (std::fabs(p->tp_coef[10]) - others) * 0.9999f;
-    }
+    true_peak_design(8, p->tp_coef, p->tp_gain, p->tp_floor);  // the reference's default oversample (loudness.py:81)
 
     // loudness framing (analysis/loudness.py:35-38 and pyloudnorm block bounds)
     auto rms_frame = [&](double seconds) {
@@ -374,11 +341,14 @@ extern "C" {
 int ta_abi_version(void) { return TA_ABI_VERSION; }
 const char* ta_last_error(void) { return g_last_error.c_str(); }
 
-int ta_plan_create(const ta_plan_desc* desc, ta_plan** out) {
+int ta_plan_create(const ta_plan_desc* desc, ta_plan** out) { return ta_plan_create_window(desc, nullptr, out); }
+
+int ta_plan_create_window(const ta_plan_desc* desc, const double* window, ta_plan** out) {
     TA_REQUIRE(desc && out, "desc/out must not be NULL");
     *out = nullptr;
-    TA_REQUIRE(desc->n_fft == 1024 || desc->n_fft == 2048 || desc->n_fft == 4096, "n_fft must be 1024, 2048 or 4096");
-    TA_REQUIRE(desc->hop > 0 && desc->hop % 4 == 0, "hop must be a positive multiple of 4");
+    TA_REQUIRE(desc->n_fft == 256 || desc->n_fft == 512 || desc->n_fft == 1024 || desc->n_fft == 2048 || desc->n_fft == 4096,
+               "n_fft must be a power of two between 256 and 4096");
+    TA_REQUIRE(desc->hop > 0, "hop must be positive");
     TA_REQUIRE(desc->sample_rate > 0, "sample_rate must be positive");
     TA_REQUIRE(desc->n_mels >= 0 && desc->n_mels <= 1024, "n_mels out of range");
     TA_REQUIRE(desc->roll_percent > 0.0 && desc->roll_percent < 1.0, "roll_percent must be in (0,1)");
@@ -393,7 +363,7 @@ int ta_plan_create(const ta_plan_desc* desc, ta_plan** out) {
     ta_plan* p = new (std::nothrow) ta_plan();
     TA_REQUIRE(p, "out of host memory");
     p->desc = *desc;
-    int rc = plan_build(p);
+    int rc = plan_build(p, window);
     if (rc == TA_OK && cudaStreamCreateWithFlags(&p->aux_stream, cudaStreamNonBlocking) != cudaSuccess) {
         set_error("cudaStreamCreateWithFlags failed");
         rc = TA_ERR_CUDA;
@@ -433,7 +403,7 @@ int ta_plan_table(const ta_plan* plan, int which, void* host_out, size_t bytes) 
     size_t need = 0;
     double coefs[12];
     switch (which) {
-        case 0: src = plan->h_window.data(); need = plan->h_window.size() * sizeof(float); break;
+        case 0: src = plan->h_window.data(); need = size_t(plan->desc.n_fft) * sizeof(float); break;
         case 1: src = plan->h_mel_dense.data(); need = plan->h_mel_dense.size() * sizeof(float); break;
         case 2: src = plan->h_freqs.data(); need = plan->h_freqs.size() * sizeof(double); break;
         case 3: {
@@ -722,6 +692,115 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
 int ta_frontend_run(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out, void* workspace,
                     size_t workspace_bytes, void* stream) {
     return frontend_impl(plan, batch, out, workspace, workspace_bytes, stream, nullptr);
+}
+
+// ---- host-buffer entry point ------------------------------------------------------------------------------------
+namespace {
+struct DevAllocs {   // stream-ordered allocations of one ta_frontend_run_host call, released on every exit path
+    cudaStream_t st;
+    std::vector<void*> ptrs;
+    explicit DevAllocs(cudaStream_t s) : st(s) {}
+    void* get(size_t bytes) {
+        void* p = nullptr;
+        if (cudaMallocAsync(&p, std::max<size_t>(bytes, 16), st) != cudaSuccess) return nullptr;
+        ptrs.push_back(p);
+        return p;
+    }
+    ~DevAllocs() {
+        for (void* p : ptrs) cudaFreeAsync(p, st);
+    }
+};
+}  // namespace
+
+int ta_frontend_run_host(const ta_plan* plan, const ta_batch* hbatch, const ta_frontend_out* hout, void* stream) {
+    TA_REQUIRE(plan && hbatch && hout, "plan/batch/out must not be NULL");
+    TA_REQUIRE(hbatch->n_tracks > 0 && hbatch->pcm && hbatch->pcm_offset && hbatch->n_samples, "batch pointers must not be NULL");
+    TA_REQUIRE(hbatch->channels == 1 || hbatch->channels == 2, "channels must be 1 or 2");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TA_CUDA(cudaSetDevice(plan->desc.device));
+    DevAllocs mem(st);
+    // PCM span on the host -> one device buffer with the same element offsets
+    int64_t span = 0;
+    for (int i = 0; i < hbatch->n_tracks; ++i) {
+        TA_REQUIRE(hbatch->n_samples[i] >= 0 && hbatch->pcm_offset[i] >= 0, "n_samples / pcm_offset must be >= 0");
+        span = std::max<int64_t>(span, hbatch->pcm_offset[i] + int64_t(hbatch->channels) * hbatch->n_samples[i]);
+    }
+    float* d_pcm = reinterpret_cast<float*>(mem.get(size_t(span) * sizeof(float)));
+    if (!d_pcm) return cuda_fail(cudaGetLastError(), "cudaMallocAsync(pcm)", __FILE__, __LINE__);
+    if (span) TA_CUDA(cudaMemcpyAsync(d_pcm, hbatch->pcm, size_t(span) * sizeof(float), cudaMemcpyHostToDevice, st));
+    ta_batch dbatch = *hbatch;
+    dbatch.pcm = d_pcm;
+    HostBatch hb;
+    int rc = build_host_batch(plan, &dbatch, hb);
+    if (rc != TA_OK) return rc;
+    const size_t P = size_t(hb.total_pitch), nt = size_t(hb.n_tracks), B = size_t(plan->n_bins), M = size_t(plan->desc.n_mels);
+    const size_t W = size_t(std::max(2, plan->desc.tempogram_win));
+    const bool want_cqt = hout->chroma_cqt || hout->cqt_mag || hout->cqt_tuning;
+    size_t Pc = 0;
+    if (want_cqt) {
+        if ((rc = cqt_supported(plan)) != TA_OK) return rc;
+        for (auto& t : hb.tracks) Pc += size_t(ta_frame_pitch(cqt_frame_count(plan, t.n_samples)));
+    }
+    // dependency closure: buffers the schedule needs on the device although the caller did not ask for them
+    const bool w_tempo = hout->tempogram, w_ac = hout->autocorr, w_env = hout->onset_env || w_ac || w_tempo;
+    const bool w_mel = hout->mel || w_env || hout->flux_linear || hout->mfcc;
+    const bool w_chroma = hout->chroma || hout->tuning;
+    const bool w_hpss = hout->hpss_harmonic || hout->hpss_percussive;
+    const bool w_mag = hout->magnitude || w_chroma || w_hpss || want_cqt;
+    const bool w_fmax = hout->frame_max || w_chroma || want_cqt;
+    ta_frontend_out d{};
+    d.kw_pitch = hout->kw_pitch;
+    d.rms_pitch = hout->rms_pitch;
+    d.true_peak_oversample = hout->true_peak_oversample;
+    struct Copy { void* host; void* dev; size_t bytes; };
+    std::vector<Copy> copies;
+    bool oom = false;
+    auto want = [&](bool need, void* host, size_t bytes) -> void* {
+        if (!need && !host) return nullptr;
+        void* p = mem.get(bytes);
+        if (!p) { oom = true; return nullptr; }
+        if (host) copies.push_back({host, p, bytes});
+        return p;
+    };
+    d.magnitude = (float*)want(w_mag, hout->magnitude, B * P * 4);
+    d.mel = (float*)want(w_mel, hout->mel, M * P * 4);
+    d.onset_env = (float*)want(w_env, hout->onset_env, P * 4);
+    d.autocorr = (double*)want(false, hout->autocorr, P * 8);
+    d.flux_linear = (double*)want(false, hout->flux_linear, P * 8);
+    d.ltas = (double*)want(false, hout->ltas, nt * B * 8);
+    d.centroid = (double*)want(false, hout->centroid, P * 8);
+    d.rolloff_bin = (int32_t*)want(false, hout->rolloff_bin, P * 4);
+    d.band_energy = (double*)want(false, hout->band_energy, nt * 2 * B * 8);
+    d.moments = (double*)want(false, hout->moments, nt * TA_N_MOMENTS * 8);
+    d.kw_blocks = (double*)want(false, hout->kw_blocks, nt * size_t(std::max(1, hout->kw_pitch)) * 8);
+    d.lufs = (double*)want(false, hout->lufs, nt * 8);
+    d.rms_momentary = (double*)want(false, hout->rms_momentary, nt * size_t(std::max(1, hout->rms_pitch)) * 8);
+    d.rms_short = (double*)want(false, hout->rms_short, nt * size_t(std::max(1, hout->rms_pitch)) * 8);
+    d.frame_max = (float*)want(w_fmax, hout->frame_max, P * 4);
+    d.chroma = (float*)want(w_chroma, hout->chroma, 12 * P * 4);
+    d.tuning = (double*)want(w_chroma, hout->tuning, nt * 8);
+    d.tempogram = (float*)want(false, hout->tempogram, W * P * 4);
+    d.true_peak = (float*)want(false, hout->true_peak, nt * 4);
+    d.hpss_harmonic = (float*)want(w_hpss, hout->hpss_harmonic, P * 4);
+    d.hpss_percussive = (float*)want(w_hpss, hout->hpss_percussive, P * 4);
+    d.hpss_scratch = (float*)want(w_hpss, nullptr, B * P * 4);
+    d.mfcc = (double*)want(false, hout->mfcc, size_t(TA_N_MFCC) * P * 8);
+    d.chroma_cqt = (float*)want(want_cqt, hout->chroma_cqt, 12 * Pc * 4);
+    d.cqt_tuning = (double*)want(want_cqt, hout->cqt_tuning, nt * 8);
+    d.cqt_mag = (float*)want(false, hout->cqt_mag, 252 * Pc * 4);
+    if (want_cqt) {
+        d.cqt_scratch_bytes = cqt_scratch_bytes(plan, hb);
+        d.cqt_scratch = want(true, nullptr, size_t(d.cqt_scratch_bytes));
+    }
+    Workspace ws;
+    const size_t ws_bytes = carve_workspace(plan, hb, nullptr, ws);
+    void* d_ws = mem.get(ws_bytes);
+    if (oom || !d_ws) return cuda_fail(cudaGetLastError(), "cudaMallocAsync(outputs)", __FILE__, __LINE__);
+    rc = frontend_impl(plan, &dbatch, &d, d_ws, ws_bytes, stream, nullptr);
+    if (rc != TA_OK) return rc;
+    for (const Copy& c : copies) TA_CUDA(cudaMemcpyAsync(c.host, c.dev, c.bytes, cudaMemcpyDeviceToHost, st));
+    TA_CUDA(cudaStreamSynchronize(st));
+    return TA_OK;
 }
 
 int ta_frontend_run_profiled(const ta_plan* plan, const ta_batch* batch, const ta_frontend_out* out, void* workspace,

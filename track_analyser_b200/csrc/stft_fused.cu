@@ -5,6 +5,7 @@
 namespace ta {
 
 int stft_tile_frames(int n_fft) { return n_fft == 4096 ? 8 : (n_fft == 2048 ? 16 : 32); }
+int stft_transform_length(int n_fft) { return n_fft < 1024 ? 1024 : n_fft; }
 
 int run_stft_features(const ta_plan* plan, const HostBatch& hb, const Workspace& ws,
                       const ta_frontend_out* out, cudaStream_t stream) {
@@ -42,6 +43,8 @@ int run_stft_features(const ta_plan* plan, const HostBatch& hb, const Workspace&
     const int m = plan->desc.n_fft / 16;
     const int sh = (p.hop % m == 0) ? p.hop / m : 0;
     switch (plan->desc.n_fft) {
+        case 512: return launch_stft_small(plan, p, stereo, 2, stream);
+        case 256: return launch_stft_small(plan, p, stereo, 4, stream);
         case 2048: return launch_stft_n2048(plan, p, stereo, sh, stream);
         case 1024: return launch_stft_n1024(plan, p, stereo, sh, stream);
         case 4096: return launch_stft_n4096(plan, p, stereo, sh, stream);

@@ -43,12 +43,14 @@ __device__ __forceinline__ void group_barrier(int g, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
 }
 
-template <int N, int TF, bool STEREO>
+// D > 1: the plan's n_fft is N / D (256 or 512 on the 1024-point transform): the frame fills the first n_fft rows of the
+// transform (the window table is zero beyond them) and its spectrum is every D-th bin of the zero-padded transform.
+template <int N, int TF, bool STEREO, int D = 1>
 struct StftCfg {
     using C = FftCfg<N>;
     static constexpr int THREADS = 512;
     static constexpr int NG = THREADS / C::M;     // transform groups per CTA
-    static constexpr int B = N / 2 + 1;
+    static constexpr int B = N / (2 * D) + 1;     // bins of the plan's n_fft
     static constexpr int FPS = STEREO ? 2 : 4;    // frames per slot (two packed transforms)
     static constexpr int SLOTS = TF / FPS;
     static constexpr int TFP = TF + 2;            // tile row pitch (floats)
@@ -130,11 +132,12 @@ __device__ __noinline__ int rolloff_chain(const float* __restrict__ col, float* 
 
 // SH > 0: hop == SH * (N/16), so frame q of a slot reads the samples of frame 0 shifted by q*SH rows of the
 // (16, N/16) sample matrix and each thread loads 16 + (frames-1)*SH values per channel instead of 16 per frame.
-template <int N, int TF, bool STEREO, int SH>
+template <int N, int TF, bool STEREO, int SH, int D = 1>
 __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) {
     using namespace p2;
     using C = FftCfg<N>;
-    using S = StftCfg<N, TF, STEREO>;
+    using S = StftCfg<N, TF, STEREO, D>;
+    static_assert(D == 1 || (SH == 0 && C::NB >= 2), "zero-padded transforms use the generic load path of the paired core");
     using E = Ex<N>;
     constexpr int M = C::M, NG = S::NG, B = S::B, TFP = S::TFP, HP = S::HP, NACC = S::NACC, CH = S::CH;
 
@@ -198,9 +201,9 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
                 int k;
                 if constexpr (C::NB >= 2) k = Pair3<N>::owned_bin(r, i);
                 else k = kept_bin<N>(r, i);
-                atomicAdd(&p.band_energy[(size_t(t) * 2 + 1) * B + k], double(acc_s[i]));
+                if (D == 1 || k % D == 0) atomicAdd(&p.band_energy[(size_t(t) * 2 + 1) * B + k / D], double(acc_s[i]));
             }
-            if (r == 0) atomicAdd(&p.band_energy[(size_t(t) * 2 + 1) * B + N / 2], double(acc_s[8]));
+            if (r == 0) atomicAdd(&p.band_energy[(size_t(t) * 2 + 1) * B + N / (2 * D)], double(acc_s[8]));
         }
 #pragma unroll
         for (int i = 0; i < 9; ++i) acc_s[i] = 0.f;
@@ -230,7 +233,7 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
         for (int s = g; s < S::SLOTS; s += NG) {
             const int f = s * S::FPS;                // first frame of the slot inside the tile
             const int t = t0 + f;                    // absolute frame
-            const long long base = (long long)t * p.hop - N / 2;
+            const long long base = (long long)t * p.hop - N / (2 * D);
             C2 v[16];
             constexpr int NFR = S::FPS;  // frames per slot
             const bool interior = t + NFR - 1 < td.n_frames && base >= 0 && base + (long long)(NFR - 1) * p.hop + N <= td.n_samples;
@@ -303,7 +306,9 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
             pass2<N>(v, r, tw2s, ex);
             group_barrier(g, M);
             // one lower-half bin (row k of the tile) from its spectrum value and its mirror value
-            auto emit = [&](int k, const C2& zk, const C2& zn, float& side_acc) {
+            auto emit = [&](int kt, const C2& zk, const C2& zn, float& side_acc) {
+                if (D > 1 && kt % D) return;   // not a bin of the plan's n_fft
+                const int k = kt / D;
                 C2 xa, xb;
                 split_pair(zk, zn, xa, xb);
                 const float2 pa = pfma(xa.re, xa.re, pmul(xa.im, xa.im));
@@ -474,10 +479,10 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
     flush(trk);
 }
 
-template <int N, int TF, bool STEREO, int SH>
+template <int N, int TF, bool STEREO, int SH, int D = 1>
 static int launch_stft(const ta_plan* plan, StftParams p, cudaStream_t stream) {
-    using S = StftCfg<N, TF, STEREO>;
-    auto kern = stft_fused_kernel<N, TF, STEREO, SH>;
+    using S = StftCfg<N, TF, STEREO, D>;
+    auto kern = stft_fused_kernel<N, TF, STEREO, SH, D>;
     size_t smem = S::fixed + S::mel_tab_bytes(p.n_mels);
     p.mel_in_smem = (smem + S::mel_w_bytes(p.mel_nnz) <= SMEM_LIMIT) ? 1 : 0;
     if (p.mel_in_smem) smem += S::mel_w_bytes(p.mel_nnz);

@@ -34,6 +34,7 @@ struct StftParams {
 
 // sh = hop / (n_fft/16) when that is 1, 2 or 4 (frames of a slot then share loaded samples), else 0
 int launch_stft_n1024(const ta_plan* plan, const StftParams& p, bool stereo, int sh, cudaStream_t stream);
+int launch_stft_small(const ta_plan* plan, const StftParams& p, bool stereo, int d, cudaStream_t stream);
 int launch_stft_n2048(const ta_plan* plan, const StftParams& p, bool stereo, int sh, cudaStream_t stream);
 int launch_stft_n4096(const ta_plan* plan, const StftParams& p, bool stereo, int sh, cudaStream_t stream);
 

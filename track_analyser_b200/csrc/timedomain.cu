@@ -492,7 +492,7 @@ static StageU make_stage(const Biquad& b, double* lane_pow /* [32][4] */) {
 }
 
 void kw_block_bounds(const ta_plan* plan, int64_t n_samples, std::vector<int64_t>& lo, std::vector<int64_t>& hi);
-int run_true_peak(const ta_plan* plan, const HostBatch& hb, const Workspace& ws, float* true_peak, cudaStream_t stream);
+int run_true_peak(const ta_plan* plan, const HostBatch& hb, const Workspace& ws, float* true_peak, int oversample, cudaStream_t stream);
 
 // Largest granule that divides every gating-block bound of a track of `max_samples` samples.
 int kw_granule_for(const ta_plan* plan, int64_t max_samples) {
@@ -587,7 +587,7 @@ int run_time_domain(const ta_plan* plan, const HostBatch& hb, const Workspace& w
     TA_CUDA(cudaGetLastError());
 
     if (out->true_peak) {
-        int rc = run_true_peak(plan, hb, ws, out->true_peak, stream);
+        int rc = run_true_peak(plan, hb, ws, out->true_peak, out->true_peak_oversample > 0 ? out->true_peak_oversample : 8, stream);
         if (rc != TA_OK) return rc;
     }
 

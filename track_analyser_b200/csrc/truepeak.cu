@@ -9,9 +9,14 @@
 // and is skipped: the result is exact, and the 161 MAC per sample are spent only near the loud passages.  The
 // per-step maxima and M come for free from the time-domain pass (timedomain.cu).
 // One warp per step, 8 consecutive input samples (64 outputs) per lane.
+#include <algorithm>
+#include <cmath>
+
 #include "common.cuh"
 
 namespace ta {
+
+static constexpr int TP_MAX_UP = 32;
 
 struct TpParams {
     const TrackDesc* tracks;
@@ -24,10 +29,14 @@ struct TpParams {
     const uint32_t* absmax_bits;
     float* true_peak;             // [n_tracks], zero-initialised, updated with atomicMax on the float bits
     float ratio;                  // g0 / G
-    float coef[8 * 21];
+    int up;                       // oversampling factor (<= TP_MAX_UP)
+    float coef[TP_MAX_UP * 21];
 };
 
+// UPT: compile-time oversampling factor (8, the reference's default: fully unrolled) or 0 = p.up at run time.
+template <int UPT>
 __global__ void __launch_bounds__(256) true_peak_kernel(const __grid_constant__ TpParams p) {
+    const int up = UPT ? UPT : p.up;
     const int lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * 8 + (threadIdx.x >> 5), nw = (long long)gridDim.x * 8;
     for (long long w = gw; w < p.total_blocks; w += nw) {
@@ -58,7 +67,7 @@ __global__ void __launch_bounds__(256) true_peak_kernel(const __grid_constant__ 
         }
         float best = 0.f;
 #pragma unroll
-        for (int ph = 0; ph < 8; ++ph) {
+        for (int ph = 0; ph < (UPT ? UPT : up); ++ph) {
             float y[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) y[u] = 0.f;
@@ -78,7 +87,58 @@ __global__ void __launch_bounds__(256) true_peak_kernel(const __grid_constant__ 
     }
 }
 
-int run_true_peak(const ta_plan* plan, const HostBatch& hb, const Workspace& ws, float* true_peak, cudaStream_t stream) {
+// scipy.signal.resample_poly(x, up, 1): h = firwin(20 up + 1, 1 / up, window=("kaiser", 5.0)) cast to float32 (scipy matches
+// the dtype of x), scaled by up; y[up q + ph] = sum_{i=-10..10} c[ph][i + 10] x[q - i].  gain = max_ph sum |c[ph][.]| (a bound on
+// |y| / max |x|), floor = |c[0][0]| - sum_{i != 0} |c[0][i]| (|y| at the largest sample is at least floor * |x|).
+void true_peak_design(int up, float* coef /* [up * 21] */, float& gain, float& floor_) {
+    const double PI = 3.14159265358979323846;
+    auto bessel_i0 = [](double x) {
+        double s = 1.0, t = 1.0;
+        for (int k = 1; k < 200; ++k) {
+            t *= (x * 0.5) * (x * 0.5) / (double(k) * double(k));
+            s += t;
+            if (t < 1e-18 * s) break;
+        }
+        return s;
+    };
+    if (up == 1) {  // the reference takes max |x| itself (loudness.py:92-93)
+        for (int i = 0; i < 21; ++i) coef[i] = (i == 10) ? 1.f : 0.f;
+        gain = 1.0001f;
+        floor_ = 0.9999f;
+        return;
+    }
+    const int HL = 10 * up, NT = 2 * HL + 1;
+    const double fc = 1.0 / up, beta = 5.0;
+    std::vector<double> h(NT);
+    double sum = 0.0;
+    for (int n = 0; n < NT; ++n) {
+        const double m = double(n - HL);
+        const double sinc = (m == 0.0) ? 1.0 : std::sin(PI * fc * m) / (PI * fc * m);
+        const double r = m / double(HL);
+        h[n] = fc * sinc * bessel_i0(beta * std::sqrt(std::max(0.0, 1.0 - r * r))) / bessel_i0(beta);
+        sum += h[n];
+    }
+    gain = 0.f;
+    for (int ph = 0; ph < up; ++ph) {
+        float g = 0.f;
+        for (int i = -10; i <= 10; ++i) {
+            const int idx = HL + ph + up * i;
+            const float c = (idx >= 0 && idx < NT) ? float(h[idx] / sum) * float(up) : 0.f;
+            coef[ph * 21 + (i + 10)] = c;
+            g += std::fabs(c);
+        }
+        gain = std::max(gain, g);
+    }
+    float others = 0.f;
+    for (int i = -10; i <= 10; ++i)
+        if (i != 0) others += std::fabs(coef[i + 10]);
+    gain *= 1.0001f;                                        // margins cover float32 accumulation
+    floor_ = (std::fabs(coef[10]) - others) * 0.9999f;
+}
+
+int run_true_peak(const ta_plan* plan, const HostBatch& hb, const Workspace& ws, float* true_peak, int oversample,
+                  cudaStream_t stream) {
+    TA_REQUIRE(oversample >= 1 && oversample <= TP_MAX_UP, "true-peak oversample must lie in 1 .. 32");
     TpParams p{};
     p.tracks = ws.d_tracks;
     p.n_tracks = hb.n_tracks;
@@ -87,8 +147,15 @@ int run_true_peak(const ta_plan* plan, const HostBatch& hb, const Workspace& ws,
     p.blk_absmax = ws.d_blk_absmax;
     p.absmax_bits = ws.d_absmax_bits;
     p.true_peak = true_peak;
-    p.ratio = plan->tp_floor / plan->tp_gain;
-    for (int i = 0; i < 8 * 21; ++i) p.coef[i] = plan->tp_coef[i];
+    p.up = oversample;
+    if (oversample == 8) {
+        p.ratio = plan->tp_floor / plan->tp_gain;
+        for (int i = 0; i < 8 * 21; ++i) p.coef[i] = plan->tp_coef[i];
+    } else {
+        float gain, floor_;
+        true_peak_design(oversample, p.coef, gain, floor_);
+        p.ratio = floor_ > 0.f ? floor_ / gain : 0.f;   // 0: no step can be ruled out, every one is evaluated
+    }
     // per-track first step index (global step numbering of the grid-stride loop)
     std::vector<long long> begin(hb.n_tracks);
     long long total = 0;
@@ -102,7 +169,8 @@ int run_true_peak(const ta_plan* plan, const HostBatch& hb, const Workspace& ws,
     p.blk_begin = d_begin;
     if (total == 0) return TA_OK;
     const int grid = int(std::min<long long>((total + 7) / 8, (long long)plan->sm_count * 8));
-    true_peak_kernel<<<grid, 256, 0, stream>>>(p);
+    if (oversample == 8) true_peak_kernel<8><<<grid, 256, 0, stream>>>(p);
+    else true_peak_kernel<0><<<grid, 256, 0, stream>>>(p);
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TA_OK;

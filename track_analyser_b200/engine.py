@@ -99,7 +99,8 @@ class Plan:
     def __init__(self, sample_rate: int, n_fft: int = 2048, hop: int = 512, n_mels: int = 128,
                  device: int | None = None, fmin: float = 0.0, fmax: float | None = None,
                  roll_percent: float = 0.85, meter_block: float = 0.4, n_chroma: int = 12,
-                 tempogram_win: int = 384):
+                 tempogram_win: int = 384, window=None):
+        """``window``: None (periodic Hann) or n_fft float64 values, e.g. scipy.signal.get_window(name, n_fft, fftbins=True)."""
         self.tempogram_win = int(tempogram_win)
         if not torch.cuda.is_available():
             raise RuntimeError("track_analyser_b200 needs a CUDA device (B200); there is no CPU fallback")
@@ -111,7 +112,13 @@ class Plan:
                             int(tempogram_win), 0, float(fmin), float(fmax) if fmax else 0.0,
                             self.roll_percent, self.meter_block)
         handle = C.c_void_p()
-        nat.check(self.lib.ta_plan_create(C.byref(desc), C.byref(handle)))
+        if window is None:
+            nat.check(self.lib.ta_plan_create(C.byref(desc), C.byref(handle)))
+        else:
+            w = np.ascontiguousarray(window, dtype=np.float64)
+            if w.shape != (int(n_fft),):
+                raise ValueError(f"window must hold n_fft = {n_fft} values")
+            nat.check(self.lib.ta_plan_create_window(C.byref(desc), w.ctypes.data_as(C.POINTER(C.c_double)), C.byref(handle)))
         self._h = handle
         self.n_bins = self.n_fft // 2 + 1
         self._ws = None  # cached workspace tensor
@@ -176,7 +183,7 @@ class DeviceBatch:
         self.pitch = (self.n_frames + 31) & ~31
         self.pitch_off = np.concatenate([[0], np.cumsum(self.pitch)]).astype(np.int64)
         self.total_pitch = int(self.pitch_off[-1])
-        self.c_batch = nat.Batch(self.n_tracks, channels, pcm.data_ptr(),
+        self.c_batch = nat.Batch(self.n_tracks, channels, pcm.data_ptr() if hasattr(pcm, "data_ptr") else pcm.ctypes.data,
                                  self.offsets.ctypes.data_as(C.POINTER(C.c_int64)),
                                  self.n_samples.ctypes.data_as(C.POINTER(C.c_int64)))
 
@@ -262,7 +269,7 @@ def decode_pcm(raw: torch.Tensor, fmt: str, channels: int, out: torch.Tensor | N
 class FrontendBuffers:
     """Device output buffers (torch-owned) for one DeviceBatch and the matching C struct."""
 
-    def __init__(self, batch: DeviceBatch, outputs: Iterable[str]):
+    def __init__(self, batch: DeviceBatch, outputs: Iterable[str], true_peak_oversample: int = 8):
         plan = batch.plan
         dev = batch.pcm.device
         P, nt, B, M = batch.total_pitch, batch.n_tracks, plan.n_bins, plan.n_mels
@@ -319,6 +326,7 @@ class FrontendBuffers:
             self.cqt_scratch = torch.empty(need, dtype=torch.uint8, device=dev)
             self.c_out.cqt_scratch = self.cqt_scratch.data_ptr()
             self.c_out.cqt_scratch_bytes = need
+        self.c_out.true_peak_oversample = int(true_peak_oversample)
         self.c_out.kw_pitch = self.kw_pitch
         self.c_out.rms_pitch = self.rms_pitch
         self.outputs = outputs
@@ -430,15 +438,69 @@ def lazy_results(batch: DeviceBatch, bufs: FrontendBuffers) -> list[TrackResult]
 
 
 def analyse_batch(plan: Plan, tracks: Sequence[np.ndarray], outputs: Iterable[str] = DEFAULT_OUTPUTS,
-                  lazy: bool = False, resident: DeviceBatch | None = None) -> list[TrackResult]:
+                  lazy: bool = False, resident: DeviceBatch | None = None, true_peak_oversample: int = 8) -> list[TrackResult]:
     """Host arrays in, host results out: H2D copy, fused frontend, D2H copy (on first access with ``lazy``).
 
     ``resident``: a DeviceBatch that already holds exactly these tracks (uploaded for another plan); its PCM is
     reused instead of being packed and copied again."""
     batch = upload(plan, tracks) if resident is None else resident.rebind(plan)
-    bufs = FrontendBuffers(batch, outputs)
+    bufs = FrontendBuffers(batch, outputs, true_peak_oversample=true_peak_oversample)
     run_device(plan, batch, bufs)
     return lazy_results(batch, bufs) if lazy else download(batch, bufs)
+
+
+def _output_specs(plan: Plan, batch: DeviceBatch, kw_pitch: int, rms_pitch: int, Pc: int) -> dict:
+    """name -> (element count, numpy dtype) of every ta_frontend_out array (include/ta_b200.h)."""
+    P, nt, B, M = batch.total_pitch, batch.n_tracks, plan.n_bins, plan.n_mels
+    f32, f64, i32 = np.float32, np.float64, np.int32
+    return {
+        "magnitude": (B * P, f32), "mel": (M * P, f32), "onset_env": (P, f32), "autocorr": (P, f64), "flux_linear": (P, f64),
+        "ltas": (nt * B, f64), "centroid": (P, f64), "rolloff_bin": (P, i32), "band_energy": (nt * 2 * B, f64),
+        "moments": (nt * N_MOMENTS, f64), "kw_blocks": (nt * kw_pitch, f64), "lufs": (nt, f64),
+        "rms_momentary": (nt * rms_pitch, f64), "rms_short": (nt * rms_pitch, f64), "frame_max": (P, f32),
+        "chroma": (12 * P, f32), "tuning": (nt, f64), "tempogram": (plan.tempogram_win * P, f32), "true_peak": (nt, f32),
+        "hpss_harmonic": (P, f32), "hpss_percussive": (P, f32), "mfcc": (N_MFCC * P, f64),
+        "chroma_cqt": (12 * Pc, f32), "cqt_tuning": (nt, f64), "cqt_mag": (N_CQT_BINS * Pc, f32),
+    }
+
+
+def analyse_host(plan: Plan, tracks: Sequence[np.ndarray], outputs: Iterable[str] = DEFAULT_OUTPUTS,
+                 true_peak_oversample: int = 8) -> list[TrackResult]:
+    """numpy in, numpy out through ``ta_frontend_run_host``: the library owns every device buffer of the call (no torch
+    tensor is created here).  Same results as ``analyse_batch``; meant for callers that bind the C ABI without torch."""
+    tracks = [np.asarray(t, dtype=np.float32) for t in tracks]
+    chans = {1 if t.ndim == 1 else t.shape[0] for t in tracks}
+    if len(chans) != 1 or next(iter(chans)) not in (1, 2):
+        raise ValueError("a batch must hold tracks that are all mono (N,) / (1, N) or all stereo (2, N)")
+    channels = next(iter(chans))
+    host, offsets, n_samples = pack_host(tracks, channels, pinned=False)
+    pcm = host.numpy()
+    batch = DeviceBatch(plan, pcm, offsets, n_samples, channels)
+    outputs = tuple(outputs)
+    unknown = set(outputs) - set(ALL_OUTPUTS)
+    if unknown:
+        raise ValueError(f"unknown outputs {sorted(unknown)}")
+    max_ns = int(batch.n_samples.max()) if batch.n_tracks else 0
+    kw_pitch = max(1, plan.kw_block_count(max_ns))
+    rms_pitch = 1 + max_ns // plan.rms_frames(plan.meter_block)[1]
+    Pc = int(batch.cqt_layout()[2][-1]) if set(outputs) & {"chroma_cqt", "cqt_mag", "cqt_tuning"} else 0
+    specs = _output_specs(plan, batch, kw_pitch, rms_pitch, Pc)
+    host_out = {k: np.empty(specs[k][0], dtype=specs[k][1]) for k in outputs}
+    c_out = nat.FrontendOut()
+    for k, v in host_out.items():
+        setattr(c_out, k, v.ctypes.data)
+    c_out.kw_pitch, c_out.rms_pitch, c_out.true_peak_oversample = kw_pitch, rms_pitch, int(true_peak_oversample)
+    nat.check(plan.lib.ta_frontend_run_host(plan._h, C.byref(batch.c_batch), C.byref(c_out), None))
+    for k in ("ltas", "band_energy", "moments", "kw_blocks", "rms_momentary", "rms_short"):
+        if k in host_out:
+            host_out[k] = host_out[k].reshape(batch.n_tracks, *({"band_energy": (2, plan.n_bins)}.get(k, (-1,))))
+    out = []
+    for i in range(batch.n_tracks):
+        r = TrackResult(n_samples=int(batch.n_samples[i]), n_frames=int(batch.n_frames[i]), channels=channels)
+        for k, h in host_out.items():
+            r.data[k] = _cut(plan, batch, i, k, h)
+        out.append(r)
+    return out
 
 
 class HostPipeline:

@@ -55,15 +55,9 @@ def _mono(samples: np.ndarray) -> np.ndarray:
     return np.mean(x, axis=0) if x.ndim > 1 else x
 
 
-def _check_window(window: str) -> None:
-    if window != "hann":
-        raise NotImplementedError("the B200 frontend implements the Hann window the reference uses")
-
-
 def compute_ltas(samples: np.ndarray, sample_rate: int, *, n_fft: int = 2_048, hop_length: int = 512,
                  window: str = "hann") -> LongTermAverageSpectrum:
-    _check_window(window)
-    res = runtime.frontend(_mono(samples), sample_rate, n_fft=n_fft, hop=hop_length, outputs=("ltas",))
+    res = runtime.frontend(_mono(samples), sample_rate, n_fft=n_fft, hop=hop_length, outputs=("ltas",), window=window)
     return LongTermAverageSpectrum(frequencies=np.fft.rfftfreq(n=n_fft, d=1.0 / sample_rate), magnitude=res["ltas"])
 
 

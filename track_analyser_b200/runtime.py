@@ -29,16 +29,22 @@ _CQT_OUTPUTS = ("chroma_cqt", "cqt_tuning", "cqt_mag")
 
 
 def get_plan(sample_rate: int, n_fft: int = 2048, hop: int = 512, n_mels: int = 128, *, roll_percent: float = 0.85,
-             meter_block: float = 0.4, device: int | None = None) -> engine.Plan:
+             meter_block: float = 0.4, device: int | None = None, window: str = "hann") -> engine.Plan:
+    """``window``: a scipy.signal.get_window name, as librosa.stft(window=...) takes it (features.py:66-79)."""
     import torch
 
     dev = torch.cuda.current_device() if (device is None and torch.cuda.is_available()) else device
-    key = (dev, int(sample_rate), int(n_fft), int(hop), int(n_mels), float(roll_percent), float(meter_block))
+    key = (dev, int(sample_rate), int(n_fft), int(hop), int(n_mels), float(roll_percent), float(meter_block), str(window))
     with _plans_lock:
         plan = _plans.get(key)
         if plan is None:
+            table = None
+            if window != "hann":
+                import scipy.signal
+
+                table = scipy.signal.get_window(window, int(n_fft), fftbins=True)
             plan = engine.Plan(sample_rate, n_fft, hop, n_mels, device=dev, roll_percent=roll_percent,
-                               meter_block=meter_block)
+                               meter_block=meter_block, window=table)
             _plans[key] = plan
             while len(_plans) > _MAX_PLANS:
                 _plans.popitem(last=False)  # dropped here; the plan closes when its last user lets go of it
@@ -113,14 +119,14 @@ def _plan_outputs(plan: engine.Plan, n_mels: int, n_samples: int, outs) -> tuple
 
 
 def frontend(samples: np.ndarray, sample_rate: int, *, n_fft: int = 2048, hop: int = 512, n_mels: int = 128,
-             roll_percent: float = 0.85, meter_block: float = 0.4, outputs=None) -> engine.TrackResult:
+             roll_percent: float = 0.85, meter_block: float = 0.4, outputs=None, window: str = "hann") -> engine.TrackResult:
     """Run (or fetch) the fused frontend for one track given as (N,), (1, N) or (2, N) float32."""
     x = np.asarray(samples, dtype=np.float32)
     if x.ndim == 2 and x.shape[0] == 1:
         x = x[0]
     cache = getattr(_local, "cache", None)
     want = tuple(outputs) if outputs is not None else None
-    plan = get_plan(sample_rate, n_fft, hop, n_mels, roll_percent=roll_percent, meter_block=meter_block)
+    plan = get_plan(sample_rate, n_fft, hop, n_mels, roll_percent=roll_percent, meter_block=meter_block, window=window)
     everything = tuple(o for o in engine.ALL_OUTPUTS if o != "cqt_mag")
     key = None
     if cache is not None:
@@ -130,13 +136,13 @@ def frontend(samples: np.ndarray, sample_rate: int, *, n_fft: int = 2048, hop: i
         if fp in cache.get("__alias__", {}):   # mono view of a stereo buffer that is (or will be) analysed
             src = cache["__alias__"][fp]
             fp = src
-        key = (fp, int(sample_rate), n_fft, hop, n_mels, float(roll_percent), float(meter_block))
+        key = (fp, int(sample_rate), n_fft, hop, n_mels, float(roll_percent), float(meter_block), str(window))
         hit = cache.get(key)
         if hit is None and src is not None:
             x = cache["__alias_buf__"][src]   # run on the stereo buffer; the result also serves the mono requests
         if hit is not None and (want is None or all(o in hit for o in _plan_outputs(plan, n_mels, x.shape[-1], want))):
             return hit
-        default_plan = (n_fft, hop, n_mels) == (2048, 512, 128)
+        default_plan = (n_fft, hop, n_mels, window) == (2048, 512, 128, "hann")
         if want is None or default_plan or hit is not None:
             outs = everything + (tuple(want) if want else ())   # one run serves every later request of the session
         else:
