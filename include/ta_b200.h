@@ -117,7 +117,8 @@ typedef struct ta_frontend_out {
     double* flux_linear;   /* [P]      onset_strength(S=mel) on linear power: structure.py:194-196 */
     double* ltas;          /* [n_tracks * B] time-mean of magnitude: features.py:80 */
     double* centroid;      /* [P]      spectral centroid, Hz: features.py:97-100 */
-    int32_t* rolloff_bin;  /* [P]      roll-off bin index k (frequency = k*sr/n_fft): features.py:116-123 */
+    int32_t* rolloff_bin;  /* [P]      roll-off bin index k (frequency = k*sr/n_fft): features.py:116-123; numpy's sequential
+                              float32 cumsum is reproduced on the magnitude matrix, so this output needs `magnitude` */
     double* band_energy;   /* [n_tracks * 2 * B] per-bin time sums of |mid|^2 then |side|^2: stereo.py:95-122 */
     double* moments;       /* [n_tracks * TA_N_MOMENTS] sum L, R, L^2, R^2, LR, mid^2, side^2, n, sum |L|, sum |R|:
                               stereo.py:62-83, loudness.py:118, harmony.py:270-282 (mono batches: L = the signal, R = 0) */

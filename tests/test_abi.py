@@ -75,5 +75,8 @@ def test_invalid_plan_arguments_are_rejected():
     bad = _native.PlanDesc(0, 44100, 1000, 512, 128, 12, 384, 0, 0.0, 0.0, 0.85, 0.4)
     assert lib.ta_plan_create(ctypes.byref(bad), ctypes.byref(handle)) == _native.TA_ERR_INVALID
     assert b"n_fft" in lib.ta_last_error()
-    bad = _native.PlanDesc(0, 44100, 2048, 510, 128, 12, 384, 0, 0.0, 0.0, 0.85, 0.4)
+    bad = _native.PlanDesc(0, 44100, 2048, 0, 128, 12, 384, 0, 0.0, 0.0, 0.85, 0.4)
+    assert lib.ta_plan_create(ctypes.byref(bad), ctypes.byref(handle)) == _native.TA_ERR_INVALID
+    assert b"hop" in lib.ta_last_error()
+    bad = _native.PlanDesc(0, 44100, 8192, 512, 128, 12, 384, 0, 0.0, 0.0, 0.85, 0.4)
     assert lib.ta_plan_create(ctypes.byref(bad), ctypes.byref(handle)) == _native.TA_ERR_INVALID

@@ -90,12 +90,13 @@ def test_host_buffer_entry_point_equals_the_device_path():
     b = engine.analyse_host(plan, tracks, outs)
     for ra, rb in zip(a, b):
         for k in outs:
-            if k in ("ltas", "band_energy"):   # float64 atomics: summation order varies from run to run
-                np.testing.assert_allclose(rb[k], ra[k], rtol=1e-6, atol=1e-9)
+            if k in ("ltas", "band_energy", "moments", "kw_blocks", "lufs", "rms_momentary", "rms_short"):
+                # sums gathered with float64 atomics: the order of the additions varies from run to run
+                np.testing.assert_allclose(rb[k], ra[k], rtol=1e-6 if k in ("ltas", "band_energy") else 1e-11, atol=1e-9, err_msg=k)
             else:
                 np.testing.assert_array_equal(rb[k], ra[k], err_msg=k)
     # a subset that needs intermediates the caller did not ask for (mel for the envelope, magnitude for the chroma)
     c = engine.analyse_host(plan, tracks[:1], ("onset_env", "chroma", "lufs"))[0]
     np.testing.assert_array_equal(c["onset_env"], a[0]["onset_env"])
     np.testing.assert_array_equal(c["chroma"], a[0]["chroma"])
-    assert c["lufs"] == a[0]["lufs"]
+    assert c["lufs"] == pytest.approx(a[0]["lufs"], abs=1e-9)

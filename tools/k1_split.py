@@ -17,6 +17,8 @@ sets = {
     "magnitude only (FFT + (a))": ("magnitude",),
     "mel only (FFT + (b))": ("mel",),
     "magnitude+mel": ("magnitude", "mel"),
+    "rolloff only (FFT + exact chain)": ("rolloff_bin",),
+    "all but rolloff": ("magnitude", "mel", "ltas", "centroid", "band_energy", "frame_max"),
     "all K1 outputs": ("magnitude", "mel", "ltas", "centroid", "rolloff_bin", "band_energy", "frame_max"),
 }
 for name, outs in sets.items():

@@ -198,58 +198,114 @@ __global__ void __launch_bounds__(256) chroma_fb_kernel(const double* __restrict
 // raw[c, t] = sum_f fb[c, f] * |X[f, t]|^2, then each frame divided by its max.  Two frames per thread (one 64-bit read of
 // the magnitude row per bin, one packed FFMA2 per chroma bin with the filterbank weight as broadcast operand), eight rows
 // in flight per thread, 256 threads per CTA sharing the track's whole filterbank in shared memory (12 x n_bins floats,
-// 49 KB at n_fft 2048, staged once): ~64 registers, four CTAs = 32 warps per SM.  (The four-frames-per-thread version
-// needed 98 registers: 13 warps per SM, 71 % long-scoreboard stalls at 48 % of the DRAM peak.)
+// 49 KB at n_fft 2048, staged once): ~64 registers.  (The four-frames-per-thread version needed 98 registers: 13 warps
+// per SM, 71 % long-scoreboard stalls at 48 % of the DRAM peak.)
+//
+// ROLL: the same walk down the frequency axis also carries librosa.feature.spectral_rolloff (features.py:116) the way
+// numpy evaluates it -- `total = np.cumsum(S, axis=-2)` is a SEQUENTIAL float32 chain per frame, the threshold is
+// float32(roll_percent) * total[-1], the answer the first bin whose running sum is not below it.  An integer decision,
+// so the chain is walked in numpy's order on the very float32 magnitudes K1 wrote: one extra FADD per bin and frame here
+// (hidden: the kernel is HBM-bound), a checkpoint of the running sum every ROLL_BLOCK bins in shared memory, and once
+// the total is known a second walk of at most ROLL_BLOCK bins from the last checkpoint below the threshold.
 #ifndef CP_ROWS
 #define CP_ROWS 8  // magnitude rows whose loads are in flight per thread
 #endif
 static constexpr int CP_THREADS = 256;
+static constexpr int ROLL_BLOCK = 128;
+static_assert(ROLL_BLOCK % CP_ROWS == 0, "checkpoints fall on row-group boundaries");
 
-__global__ void __launch_bounds__(CP_THREADS, 4) chroma_project_kernel(const TrackDesc* __restrict__ tracks,
+template <bool CHROMA, bool ROLL>
+__global__ void __launch_bounds__(CP_THREADS, 3) chroma_project_kernel(const TrackDesc* __restrict__ tracks,
                                                                        const float* __restrict__ mag, const float* __restrict__ fb,
-                                                                       float* __restrict__ out, int n_bins) {
+                                                                       float* __restrict__ out, int32_t* __restrict__ rolloff_bin,
+                                                                       float roll_percent, int n_bins) {
     using namespace p2;
-    extern __shared__ __align__(16) float wsm[];  // [n_bins * 12]
+    extern __shared__ __align__(16) float wsm[];  // CHROMA: [n_bins * 12] filterbank; ROLL: then [n_ck][2 * CP_THREADS] checkpoints
     const TrackDesc td = tracks[blockIdx.y];
     if (blockIdx.x * CP_THREADS * 2 >= td.n_frames) return;
     const int t = (blockIdx.x * CP_THREADS + threadIdx.x) * 2;
     const bool ok = t < td.n_frames;  // rows are padded to a multiple of 32 frames, so t, t+1 stay inside the row
     const float* __restrict__ col = mag + size_t(td.pitch_off) * n_bins + (ok ? t : 0);
     const float* __restrict__ w = fb + size_t(blockIdx.y) * n_bins * 12;
+    float2* ck = reinterpret_cast<float2*>(wsm + (CHROMA ? n_bins * 12 : 0)) + threadIdx.x;  // [block * CP_THREADS]
     float2 acc[12];
 #pragma unroll
     for (int c = 0; c < 12; ++c) acc[c] = make_float2(0.f, 0.f);
+    float2 run = make_float2(0.f, 0.f);   // sequential float32 running sums of the two frames
     auto accumulate = [&](const float2 m, const float* wk) {
-        const float2 s = pmul(m, m);
-        const float4 w0 = *reinterpret_cast<const float4*>(wk);
-        const float4 w1 = *reinterpret_cast<const float4*>(wk + 4);
-        const float4 w2 = *reinterpret_cast<const float4*>(wk + 8);
-        const float ww[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+        if (ROLL) {
+            run.x = __fadd_rn(run.x, m.x);
+            run.y = __fadd_rn(run.y, m.y);
+        }
+        if (CHROMA) {
+            const float2 s = pmul(m, m);
+            const float4 w0 = *reinterpret_cast<const float4*>(wk);
+            const float4 w1 = *reinterpret_cast<const float4*>(wk + 4);
+            const float4 w2 = *reinterpret_cast<const float4*>(wk + 8);
+            const float ww[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
 #pragma unroll
-        for (int c = 0; c < 12; ++c) acc[c] = pfmas(s, ww[c], acc[c]);
+            for (int c = 0; c < 12; ++c) acc[c] = pfmas(s, ww[c], acc[c]);
+        }
     };
-    for (int i = threadIdx.x; i < n_bins * 12; i += CP_THREADS) wsm[i] = w[i];
-    __syncthreads();
+    if (CHROMA) {
+        for (int i = threadIdx.x; i < n_bins * 12; i += CP_THREADS) wsm[i] = w[i];
+        __syncthreads();
+    }
     int kk = 0;
     for (; kk + CP_ROWS <= n_bins; kk += CP_ROWS) {
+        if (ROLL && kk % ROLL_BLOCK == 0) ck[(kk / ROLL_BLOCK) * CP_THREADS] = run;  // sum of bins [0, kk)
         float2 m[CP_ROWS];
 #pragma unroll
         for (int u = 0; u < CP_ROWS; ++u) m[u] = __ldg(reinterpret_cast<const float2*>(col + size_t(kk + u) * td.ld));
 #pragma unroll
         for (int u = 0; u < CP_ROWS; ++u) accumulate(m[u], wsm + (kk + u) * 12);
     }
-    for (; kk < n_bins; ++kk) accumulate(__ldg(reinterpret_cast<const float2*>(col + size_t(kk) * td.ld)), wsm + kk * 12);
-    if (!ok) return;
-    float2 mx = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int c = 0; c < 12; ++c) {
-        mx.x = fmaxf(mx.x, fabsf(acc[c].x));
-        mx.y = fmaxf(mx.y, fabsf(acc[c].y));
+    for (; kk < n_bins; ++kk) {
+        if (ROLL && kk % ROLL_BLOCK == 0) ck[(kk / ROLL_BLOCK) * CP_THREADS] = run;
+        accumulate(__ldg(reinterpret_cast<const float2*>(col + size_t(kk) * td.ld)), wsm + kk * 12);
     }
-    const float l0 = (mx.x < 1.1754943508222875e-38f) ? 1.0f : mx.x, l1 = (mx.y < 1.1754943508222875e-38f) ? 1.0f : mx.y;
-    float* dst = out + size_t(td.pitch_off) * 12 + t;
+    if (!ok) return;
+    if (ROLL) {
+        const int n_ck = (n_bins + ROLL_BLOCK - 1) / ROLL_BLOCK;
 #pragma unroll
-    for (int c = 0; c < 12; ++c) *reinterpret_cast<float2*>(dst + size_t(c) * td.ld) = make_float2(acc[c].x / l0, acc[c].y / l1);
+        for (int h = 0; h < 2; ++h) {
+            if (t + h >= td.n_frames) break;
+            const float thr = __fmul_rn(roll_percent, h ? run.y : run.x);
+            int b = 0;   // last checkpoint still below the threshold (running sums of non-negative values never decrease)
+            for (int j = 1; j < n_ck; ++j) {
+                const float2 c = ck[j * CP_THREADS];
+                if ((h ? c.y : c.x) < thr) b = j;
+            }
+            const float2 c0 = ck[b * CP_THREADS];
+            float r = h ? c0.y : c0.x;
+            int first = n_bins - 1;
+            const float* __restrict__ colh = col + h;
+            // second walk, 16 rows in flight (reading a few rows past the answer is harmless; the adds stay sequential)
+            for (int k0 = b * ROLL_BLOCK; k0 < n_bins && first == n_bins - 1; k0 += 16) {
+                float v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v[u] = __ldg(colh + size_t(min(k0 + u, n_bins - 1)) * td.ld);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    r = __fadd_rn(r, v[u]);
+                    if (first == n_bins - 1 && k0 + u < n_bins - 1 && !(r < thr)) first = k0 + u;
+                }
+            }
+            rolloff_bin[td.pitch_off + t + h] = first;
+        }
+    }
+    if (CHROMA) {
+        float2 mx = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c = 0; c < 12; ++c) {
+            mx.x = fmaxf(mx.x, fabsf(acc[c].x));
+            mx.y = fmaxf(mx.y, fabsf(acc[c].y));
+        }
+        const float l0 = (mx.x < 1.1754943508222875e-38f) ? 1.0f : mx.x, l1 = (mx.y < 1.1754943508222875e-38f) ? 1.0f : mx.y;
+        float* dst = out + size_t(td.pitch_off) * 12 + t;
+#pragma unroll
+        for (int c = 0; c < 12; ++c) *reinterpret_cast<float2*>(dst + size_t(c) * td.ld) = make_float2(acc[c].x / l0, acc[c].y / l1);
+    }
 }
 
 // workspace layout helpers ----------------------------------------------------------------
@@ -333,9 +389,31 @@ int run_tuning(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_trac
     return TA_OK;
 }
 
+template <bool CHROMA, bool ROLL>
+static int launch_project(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_tracks, const float* mag, const float* fb,
+                          float* chroma, int32_t* rolloff_bin, cudaStream_t stream) {
+    const size_t n_ck = (size_t(plan->n_bins) + ROLL_BLOCK - 1) / ROLL_BLOCK;
+    const size_t smem = (CHROMA ? size_t(plan->n_bins) * 12 * sizeof(float) : 0) + (ROLL ? n_ck * CP_THREADS * sizeof(float2) : 0);
+    auto kern = chroma_project_kernel<CHROMA, ROLL>;
+    TA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3((hb.max_frames + 2 * CP_THREADS - 1) / (2 * CP_THREADS), hb.n_tracks), CP_THREADS, smem, stream>>>(
+        d_tracks, mag, fb, chroma, rolloff_bin, float(plan->desc.roll_percent), plan->n_bins);
+    count_launch();
+    TA_CUDA(cudaGetLastError());
+    return TA_OK;
+}
+
+// chroma (may be NULL) and / or the roll-off bins (may be NULL) from an existing magnitude spectrogram
 int run_chroma(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_tracks, const float* mag, const float* frame_max,
-               float* chroma, double* tuning, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+               float* chroma, double* tuning, int32_t* rolloff_bin, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+    TA_REQUIRE(hb.n_tracks <= 65535, "at most 65535 tracks per call");
+    TA_REQUIRE(mag && (reinterpret_cast<uintptr_t>(mag) & 15) == 0, "the magnitude buffer must be present and 16-byte aligned");
+    if (!chroma) {
+        if (!rolloff_bin) return TA_OK;
+        return launch_project<false, true>(plan, hb, d_tracks, mag, nullptr, nullptr, rolloff_bin, stream);
+    }
     TA_REQUIRE(plan->desc.n_chroma == 12, "only n_chroma = 12 is implemented");
+    TA_REQUIRE(frame_max && tuning, "chroma needs the frame_max and tuning buffers");
     TA_REQUIRE(scratch && scratch_bytes >= chroma_scratch_bytes(plan, hb), "chroma scratch too small");
     int rc = run_tuning(plan, hb, d_tracks, mag, frame_max, true, 12, scratch, tuning, nullptr, stream);
     if (rc != TA_OK) return rc;
@@ -344,15 +422,9 @@ int run_chroma(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_trac
                                                                                       double(plan->desc.sample_rate));
     count_launch();
     TA_CUDA(cudaGetLastError());
-    TA_REQUIRE((reinterpret_cast<uintptr_t>(mag) & 15) == 0 && (reinterpret_cast<uintptr_t>(chroma) & 15) == 0,
-               "magnitude and chroma buffers must be 16-byte aligned");
-    const size_t fb_smem = size_t(plan->n_bins) * 12 * sizeof(float);
-    TA_CUDA(cudaFuncSetAttribute(chroma_project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fb_smem));
-    chroma_project_kernel<<<dim3((hb.max_frames + 2 * CP_THREADS - 1) / (2 * CP_THREADS), hb.n_tracks), CP_THREADS, fb_smem, stream>>>(
-        d_tracks, mag, fb, chroma, plan->n_bins);
-    count_launch();
-    TA_CUDA(cudaGetLastError());
-    return TA_OK;
+    TA_REQUIRE((reinterpret_cast<uintptr_t>(chroma) & 15) == 0, "the chroma buffer must be 16-byte aligned");
+    return rolloff_bin ? launch_project<true, true>(plan, hb, d_tracks, mag, fb, chroma, rolloff_bin, stream)
+                       : launch_project<true, false>(plan, hb, d_tracks, mag, fb, chroma, nullptr, stream);
 }
 
 }  // namespace ta

@@ -105,6 +105,7 @@ int build_host_batch(const ta_plan* plan, const ta_batch* b, HostBatch& hb);
 struct Workspace {
     TrackDesc* d_tracks;       // [n_tracks]
     uint32_t* d_mel_max;       // [n_tracks]
+    void* d_tmaps;             // [n_tracks] CUtensorMap (128 bytes each) of the magnitude matrices, K1's TMA stores
     double* d_granules;        // granule sums of the time-domain pass (three areas)
     size_t gran_doubles;
     double* d_fft;             // autocorrelation scratch (complex double) [..]

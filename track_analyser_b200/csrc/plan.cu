@@ -289,7 +289,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 size_t td_granule_doubles(const ta_plan* plan, const HostBatch& hb);
 size_t chroma_scratch_bytes(const ta_plan* plan, const HostBatch& hb);
 int run_chroma(const ta_plan*, const HostBatch&, const TrackDesc*, const float* mag, const float* frame_max, float* chroma,
-               double* tuning, void* scratch, size_t scratch_bytes, cudaStream_t);
+               double* tuning, int32_t* rolloff_bin, void* scratch, size_t scratch_bytes, cudaStream_t);
 int run_tempogram(const ta_plan*, const HostBatch&, const TrackDesc*, const float* env, float* out, cudaStream_t);
 int run_mfcc(const ta_plan*, const HostBatch&, const TrackDesc*, const float* mel, const uint32_t* mel_max, double* mfcc,
              cudaStream_t);
@@ -313,6 +313,7 @@ size_t carve_workspace(const ta_plan* plan, const HostBatch& hb, void* base, Wor
     };
     ws.d_tracks = reinterpret_cast<TrackDesc*>(take(sizeof(TrackDesc) * hb.n_tracks));
     ws.d_mel_max = reinterpret_cast<uint32_t*>(take(sizeof(uint32_t) * hb.n_tracks));
+    ws.d_tmaps = take(size_t(128) * hb.n_tracks);
     // granule sums: K-weighted, momentary hop, short-term hop
     ws.gran_doubles = td_granule_doubles(plan, hb);
     ws.d_granules = reinterpret_cast<double*>(take(sizeof(double) * ws.gran_doubles));
@@ -452,7 +453,12 @@ int ta_stft_features(const ta_plan* plan, const ta_batch* batch, const ta_fronte
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int rc = prepare(plan, batch, workspace, workspace_bytes, st, hb, ws);
     if (rc != TA_OK) return rc;
-    return run_stft_features(plan, hb, ws, out, st);
+    TA_REQUIRE(!out->rolloff_bin || out->magnitude, "rolloff_bin output needs the magnitude buffer");
+    if ((rc = run_stft_features(plan, hb, ws, out, st)) != TA_OK) return rc;
+    // the roll-off bins come from a sequential walk down the magnitude columns (chroma.cu)
+    if (out->rolloff_bin)
+        return run_chroma(plan, hb, ws.d_tracks, out->magnitude, nullptr, nullptr, nullptr, out->rolloff_bin, nullptr, 0, st);
+    return TA_OK;
 }
 
 int ta_onset_flux(const ta_plan* plan, const ta_batch* batch, const float* mel, const uint32_t* mel_max_bits,
@@ -502,7 +508,7 @@ int ta_chroma_stft(const ta_plan* plan, const ta_batch* batch, const float* magn
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int rc = prepare(plan, batch, workspace, workspace_bytes, st, hb, ws);
     if (rc != TA_OK) return rc;
-    return run_chroma(plan, hb, ws.d_tracks, magnitude, frame_max, chroma, tuning, ws.d_chroma, ws.chroma_bytes, st);
+    return run_chroma(plan, hb, ws.d_tracks, magnitude, frame_max, chroma, tuning, nullptr, ws.d_chroma, ws.chroma_bytes, st);
 }
 
 int ta_tempogram(const ta_plan* plan, const ta_batch* batch, const float* onset_env, float* tempogram, void* workspace,
@@ -606,6 +612,7 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
         return TA_ERR_INVALID;
     }
     if (out->tempogram && !out->onset_env) { join(); set_error("tempogram output needs the onset_env buffer"); return TA_ERR_INVALID; }
+    if (out->rolloff_bin && !out->magnitude) { join(); set_error("rolloff_bin output needs the magnitude buffer"); return TA_ERR_INVALID; }
     if (out->chroma_cqt || out->cqt_mag) {
         if (!(out->chroma_cqt && out->magnitude && out->frame_max && out->cqt_tuning && out->cqt_scratch)) {
             join();
@@ -625,11 +632,12 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
         return TA_ERR_INVALID;
     }
     bool chroma_done = false;
-    if (fork_mag && (out->chroma || out->hpss_harmonic || out->chroma_cqt)) {  // magnitude consumers on the second stream, behind K1
+    const bool need_proj = out->chroma || out->rolloff_bin;  // the walk down the magnitude columns: chroma and / or roll-off
+    if (fork_mag && (need_proj || out->hpss_harmonic || out->chroma_cqt)) {  // magnitude consumers on the second stream, behind K1
         cudaEventRecord(ev_k1, st);
         cudaStreamWaitEvent(aux, ev_k1, 0);
-        if (out->chroma && (rc = run_chroma(plan, hb, ws.d_tracks, out->magnitude, out->frame_max, out->chroma, out->tuning,
-                                            ws.d_chroma, ws.chroma_bytes, aux)) != TA_OK) {
+        if (need_proj && (rc = run_chroma(plan, hb, ws.d_tracks, out->magnitude, out->frame_max, out->chroma, out->tuning,
+                                          out->rolloff_bin, ws.d_chroma, ws.chroma_bytes, aux)) != TA_OK) {
             join();
             return rc;
         }
@@ -664,9 +672,9 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
     mark(3);
     if (out->tempogram && (rc = run_tempogram(plan, hb, ws.d_tracks, out->onset_env, out->tempogram, st)) != TA_OK) { join(); return rc; }
     mark(4);
-    if (out->chroma && !chroma_done &&
-        (rc = run_chroma(plan, hb, ws.d_tracks, out->magnitude, out->frame_max, out->chroma, out->tuning, ws.d_chroma,
-                         ws.chroma_bytes, st)) != TA_OK) {
+    if (need_proj && !chroma_done &&
+        (rc = run_chroma(plan, hb, ws.d_tracks, out->magnitude, out->frame_max, out->chroma, out->tuning, out->rolloff_bin,
+                         ws.d_chroma, ws.chroma_bytes, st)) != TA_OK) {
         join();
         return rc;
     }
@@ -746,7 +754,7 @@ int ta_frontend_run_host(const ta_plan* plan, const ta_batch* hbatch, const ta_f
     const bool w_mel = hout->mel || w_env || hout->flux_linear || hout->mfcc;
     const bool w_chroma = hout->chroma || hout->tuning;
     const bool w_hpss = hout->hpss_harmonic || hout->hpss_percussive;
-    const bool w_mag = hout->magnitude || w_chroma || w_hpss || want_cqt;
+    const bool w_mag = hout->magnitude || w_chroma || w_hpss || want_cqt || hout->rolloff_bin;
     const bool w_fmax = hout->frame_max || w_chroma || want_cqt;
     ta_frontend_out d{};
     d.kw_pitch = hout->kw_pitch;

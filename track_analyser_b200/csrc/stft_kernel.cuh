@@ -16,8 +16,8 @@
 //             epilogue    (a) magnitude tile -> global, row segments of TF contiguous floats;
 //                             per-bin time sums (LTAS, |mid|^2), one thread per bin
 //                         (b) sparse Slaney mel projection of tile^2 -> global (two frames per thread)
-//                         (c) per-frame centroid / roll-off / max: one warp per frame pair, one bin chunk
-//                             per lane, warp scans instead of shared-memory partials
+//                         (c) per-frame centroid / max: one warp per frame pair, one bin chunk per lane
+//                             (the roll-off bin is an exact sequential float32 chain: chroma.cu walks it)
 // Algorithmic HBM bytes per tile: read C*TF*hop*4 (PCM), write (B+M)*TF*4 + 16*TF.
 #pragma once
 #include <algorithm>
@@ -55,8 +55,7 @@ struct StftCfg {
     static constexpr int SLOTS = TF / FPS;
     static constexpr int TFP = TF + 2;            // tile row pitch (floats)
     static constexpr int HP = TF / 2;             // frame pairs per tile
-    static constexpr int ETHREADS = THREADS - 32;  // epilogue threads of parts (a), (b); the last warp walks the roll-off chains
-    static constexpr int NACC = (B + ETHREADS - 1) / ETHREADS;
+    static constexpr int NACC = (B + THREADS - 1) / THREADS;
     static constexpr int CH = (B + 31) / 32;      // bins per lane in the per-frame feature pass
     static_assert(SLOTS % NG == 0, "tile must hold a whole number of rounds");
     static_assert((TFP / 2) % 2 == 1, "tile pitch / 2 must be odd");
@@ -91,43 +90,6 @@ __device__ __forceinline__ float2 mel_taps(const float* __restrict__ col, const 
         a0 = pfmas(pmul(x0, x0), wt[j], a0);
     }
     return padd(a0, a1);
-}
-
-// Roll-off bin of one frame (column `col` of the magnitude tile, row pitch TFP), evaluated the way numpy does
-// (librosa.feature.spectral_rolloff, features.py:116): float32 cumsum = sequential additions along frequency, threshold =
-// float32(roll_percent) * total, first bin whose running sum is not below it.  `ck` (pitch TF) receives a checkpoint of
-// the running sum every 32 bins so that the second pass restarts at most 32 bins before the answer.  Not inlined: the
-// chain runs on one warp of the epilogue and must not weigh on the register allocation of the FFT phase.
-template <int B, int TF, int TFP>
-__device__ __noinline__ int rolloff_chain(const float* __restrict__ col, float* __restrict__ ck, float roll_percent) {
-    float c = 0.f;
-    int k = 0;
-    for (; k + 32 <= B; k += 32) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {   // 16 loads in flight ahead of the dependent additions
-            float x[16];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) x[u] = col[(k + 16 * h + u) * TFP];
-#pragma unroll
-            for (int u = 0; u < 16; ++u) c = __fadd_rn(c, x[u]);
-        }
-        ck[(k >> 5) * TF] = c;
-    }
-    for (; k < B; ++k) c = __fadd_rn(c, col[k * TFP]);
-    const float thr = __fmul_rn(roll_percent, c);
-    // checkpoints [0, lo) are below the threshold, [hi, NCK) are not (running sums of non-negative values never decrease)
-    constexpr int NCK = B / 32;
-    int lo = 0, hi = NCK;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (ck[mid * TF] < thr) lo = mid + 1; else hi = mid;
-    }
-    float run = lo ? ck[(lo - 1) * TF] : 0.f;
-    for (int kk = lo * 32; kk < B; ++kk) {
-        run = __fadd_rn(run, col[kk * TFP]);
-        if (!(run < thr)) return kk;
-    }
-    return B - 1;
 }
 
 // SH > 0: hop == SH * (N/16), so frame q of a slot reads the samples of frame 0 shifted by q*SH rows of the
@@ -209,8 +171,8 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
         for (int i = 0; i < 9; ++i) acc_s[i] = 0.f;
 #pragma unroll
         for (int j = 0; j < NACC; ++j) {
-            const int k = tid + S::ETHREADS * j;
-            if (tid < S::ETHREADS && k < B) {
+            const int k = tid + S::THREADS * j;
+            if (k < B) {
                 if (p.ltas) atomicAdd(&p.ltas[size_t(t) * B + k], double(acc_l[j]));
                 if (p.band_energy) atomicAdd(&p.band_energy[(size_t(t) * 2 + 0) * B + k], double(acc_m[j]));
             }
@@ -359,16 +321,6 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
         __syncthreads();
 
         // ------------------------------ epilogue ------------------------------
-        if (warp == S::THREADS / 32 - 1) {
-            // (d) roll-off, exactly as numpy evaluates it (librosa.feature.spectral_rolloff, features.py:116): the float32
-            // cumsum along frequency is a SEQUENTIAL chain of 1 + n_fft/2 additions per frame, the threshold is
-            // float32(roll_percent) * total, the answer the first bin whose running sum is not below it -- an integer
-            // decision, so the chain is walked in numpy's order: lane = frame of the tile, one pass for the total with a
-            // checkpoint every 32 bins (kept in the idle exchange buffers), then at most 32 steps from the last checkpoint
-            // below the threshold.  ~4 cycles per step on one warp, hidden behind parts (a)-(c) on the other fifteen.
-            if (p.rolloff_bin && lane < nf)
-                p.rolloff_bin[col_out(td, t0, lane)] = rolloff_chain<B, TF, TFP>(tile + lane, reinterpret_cast<float*>(ex_all) + lane, p.roll_percent);
-        } else {
         {   // (a) magnitude rows -> global (64-bit stores, TF contiguous floats per row).  A half-warp reads RPH rows
             // that are D rows apart so that its 16 64-bit words fall into 16 distinct bank pairs.
             constexpr int RPH = 16 / HP, D = (TF == 16) ? 8 : (TF == 8) ? 4 : 1, RB = D * RPH;
@@ -376,7 +328,7 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
             const bool ok0 = 2 * fp < nf, ok1 = 2 * fp + 1 < nf;
             if (p.mag) {
                 float* dst = p.mag + size_t(td.pitch_off) * B + t0 + 2 * fp;
-                for (int q = hw; (q / D) * RB < B; q += S::ETHREADS / 16) {
+                for (int q = hw; (q / D) * RB < B; q += S::THREADS / 16) {
                     const int k = (q / D) * RB + (q % D) + ri * D;
                     if (k < B && ok0) {
                         const float2 a = *reinterpret_cast<const float2*>(tile + k * TFP + 2 * fp);
@@ -389,7 +341,7 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
             if (p.ltas || p.band_energy) {
 #pragma unroll
                 for (int j = 0; j < NACC; ++j) {
-                    const int k = tid + S::ETHREADS * j;
+                    const int k = tid + S::THREADS * j;
                     if (k < B) {
                         const float* row = tile + k * TFP;
                         float2 s = make_float2(0.f, 0.f), q = s;
@@ -408,7 +360,7 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
         // (b) mel projection of tile^2 (power = magnitude**2 as librosa computes it), two frames per thread
         if (p.mel) {
             float vmax = 0.f;
-            for (int it = tid; it < p.n_mels * HP; it += S::ETHREADS) {
+            for (int it = tid; it < p.n_mels * HP; it += S::THREADS) {
                 const int fp = it % HP, m = it / HP;
                 const int ks = mel_tab[m], len = mel_tab[p.n_mels + m], wo = mel_tab[2 * p.n_mels + m];
                 const float* col = tile + ks * TFP + 2 * fp;
@@ -428,12 +380,10 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
                 if (lane == 0) atomicMax(&p.mel_max[trk], __float_as_uint(vmax));
             }
         }
-        }
-        // (c) per-frame centroid / roll-off / max: warp per frame, lane c owns bins [c*CH, c*CH+CH).
+        // (c) per-frame centroid / max: warp per frame pair, lane c owns bins [c*CH, c*CH+CH).
         // fp32 chunk sums s1 = sum |X|, s2 = sum (k-kb)|X|; centroid = df * sum_c (s2_c + kb_c*s1_c) / sum_c s1_c
         // combined in double.  (librosa rounds |X|/sum to float32 before the float64 dot product; that changes
-        // the result by ~2e-9 relative.)  Roll-off: first bin whose running float32 sum reaches 0.85*total:
-        // warp scan over the chunk sums finds the chunk, a second scan inside that chunk finds the bin.
+        // the result by ~2e-9 relative.)
         if (p.centroid || p.frame_max) {
             for (int fp = warp; 2 * fp < nf; fp += S::THREADS / 32) {   // warp per frame PAIR: one 64-bit read serves both
                 const float* col = tile + 2 * fp;

@@ -1,5 +1,7 @@
 // Parameter block of the fused STFT kernel and the per-n_fft launchers (stft_n*.cu).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace ta {
@@ -22,6 +24,7 @@ struct StftParams {
     const int* mel_woff;
     const float* mel_w;
     // outputs (nullable)
+    const CUtensorMap* tmaps;  // [n_tracks] tensor maps of the per-track (bins, T) magnitude matrices, or nullptr: no magnitude
     float* mag;
     float* mel;
     double* centroid;

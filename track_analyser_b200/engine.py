@@ -289,6 +289,8 @@ class FrontendBuffers:
             outputs.add("mel")
         if outputs & {"hpss_harmonic", "hpss_percussive"}:
             outputs |= {"hpss_harmonic", "hpss_percussive", "magnitude"}
+        if "rolloff_bin" in outputs:
+            outputs.add("magnitude")
         if outputs & {"chroma_cqt", "cqt_tuning", "cqt_mag"}:
             outputs |= {"chroma_cqt", "cqt_tuning", "magnitude", "frame_max"}
         Pc = int(batch.cqt_layout()[2][-1]) if "chroma_cqt" in outputs else 0
