@@ -306,6 +306,8 @@ struct CqtParams {
 
 __device__ __forceinline__ void cq_barrier(int g, int n) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(n) : "memory"); }
 
+// BS: bin step (1024 / n_fft of the octave transforms), a compile-time 1, 2 or 4
+template <int BS>
 __global__ void __launch_bounds__(512, 1) cqt_chroma_kernel(const CqtParams p) {
     using namespace p2;
     using C = FftCfg<CQ_N>;
@@ -328,32 +330,50 @@ __global__ void __launch_bounds__(512, 1) cqt_chroma_kernel(const CqtParams p) {
     __syncthreads();
 
     const int trk = blockIdx.y;
-    const CqtTrack td = p.tracks[trk];
+    const CqtTrack* __restrict__ tdp = p.tracks + trk;
+    struct { long long pitch_off; int n_frames, ld; } td = {tdp->pitch_off, tdp->n_frames, tdp->ld};
     const int ti = p.tuning_idx[trk];
     const int n_tiles = (td.n_frames + CQ_TF - 1) / CQ_TF;
+    const int nfft = CQ_N / BS;
     const int cfr = tid & 31, cc = tid >> 5;   // chroma owner: frame, pitch class (tid < 384)
 
     for (int w = blockIdx.x; w < n_tiles; w += gridDim.x) {
         const int t0 = w * CQ_TF, nf = min(CQ_TF, td.n_frames - t0);
         float cacc = 0.f;
         for (int oct = 0; oct < CQ_OCT; ++oct) {
-            const float* __restrict__ x = td.sig[oct];
-            const long long len = td.len[oct];
+            const float* __restrict__ x = tdp->sig[oct];
+            const long long len = tdp->len[oct];
             const int hop = p.hop0 >> oct;
             {   // four frames t .. t+3 of this group: A = frame t + i*frame t+2, B = frame t+1 + i*frame t+3
                 const int f = 4 * g, t = t0 + f;
                 C2 v[16];
+                const long long s0 = (long long)t * hop - nfft / 2 + r;   // sample of (frame t, row 0) for this thread
+                // the whole slot inside the signal and the track: unchecked loads (rows n >= nfft of a zero-padded transform
+                // are compile-time zeros)
+                if (t + 3 < td.n_frames && s0 - r >= 0 && s0 - r + 3LL * hop + nfft <= len) {
 #pragma unroll
-                for (int n1 = 0; n1 < 16; ++n1) {
-                    const int n = n1 * M + r;
-                    float xs[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const long long s = (long long)(t + q) * hop - p.nfft / 2 + n;
-                        xs[q] = (n < p.nfft && t + q < td.n_frames && s >= 0 && s < len) ? __ldg(x + s) : 0.f;
+                    for (int n1 = 0; n1 < 16; ++n1) {
+                        if (n1 * M >= nfft) {
+                            v[n1].re = v[n1].im = make_float2(0.f, 0.f);
+                        } else {
+                            const float* __restrict__ q0 = x + s0 + n1 * M;
+                            v[n1].re = pmuls(make_float2(__ldg(q0), __ldg(q0 + hop)), 0.5f);
+                            v[n1].im = pmuls(make_float2(__ldg(q0 + 2 * hop), __ldg(q0 + 3 * hop)), 0.5f);
+                        }
                     }
-                    v[n1].re = pmuls(make_float2(xs[0], xs[1]), 0.5f);
-                    v[n1].im = pmuls(make_float2(xs[2], xs[3]), 0.5f);
+                } else {
+#pragma unroll
+                    for (int n1 = 0; n1 < 16; ++n1) {
+                        const int n = n1 * M + r;
+                        float xs[4];
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const long long s = s0 + (long long)q * hop + n1 * M;
+                            xs[q] = (n < nfft && t + q < td.n_frames && s >= 0 && s < len) ? __ldg(x + s) : 0.f;
+                        }
+                        v[n1].re = pmuls(make_float2(xs[0], xs[1]), 0.5f);
+                        v[n1].im = pmuls(make_float2(xs[2], xs[3]), 0.5f);
+                    }
                 }
                 pass1<N>(v, r, tw1s, ex);
                 cq_barrier(g, M);
@@ -361,8 +381,8 @@ __global__ void __launch_bounds__(512, 1) cqt_chroma_kernel(const CqtParams p) {
                 cq_barrier(g, M);
                 pass3_paired<N>(v, r, ex);
                 auto emit = [&](int k, const C2& zk, const C2& zn) {
-                    if (k % p.bin_step) return;
-                    const int row = k / p.bin_step - p.j_lo;
+                    if (BS > 1 && k % BS) return;
+                    const int row = k / BS - p.j_lo;
                     if (row < 0 || row >= p.n_rows) return;
                     C2 xa, xb;
                     split_pair(zk, zn, xa, xb);
@@ -777,10 +797,11 @@ int run_chroma_cqt(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_
     const size_t smem = size_t(512 / (CQ_N / 16)) * E::SLOTS * 16 + size_t(15) * (CQ_N / 16) * 8 + size_t(16) * (CQ_N / 256) * 8 +
                         size_t(p.n_rows) * CQ_SPITCH * 8 + size_t(CQ_BPO) * CQ_TF * 4 + size_t(12) * CQ_TF * 4;
     TA_REQUIRE(smem <= 232448, "constant-Q spectrum tile does not fit in shared memory");
-    TA_CUDA(cudaFuncSetAttribute(cqt_chroma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = (max_frames + CQ_TF - 1) / CQ_TF;
     const int gx = std::max(1, std::min(tiles, std::max(1, (4 * plan->sm_count + nt - 1) / nt)));
-    cqt_chroma_kernel<<<dim3(gx, nt), 512, smem, stream>>>(p);
+    auto kern = t->bin_step == 1 ? cqt_chroma_kernel<1> : (t->bin_step == 2 ? cqt_chroma_kernel<2> : cqt_chroma_kernel<4>);
+    TA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(gx, nt), 512, smem, stream>>>(p);
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TA_OK;
