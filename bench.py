@@ -199,11 +199,16 @@ def reference_arm(args, rank, world):
     wall = sum(w for _, w in vals)
     v = audio / wall
     sample = f"{workers} tracks x {seconds:.0f} s per step, one process per track (oracle port, STFTs shared)"
+    cfg = workload_config(args, world)
+    # the metric is length-normalised (audio seconds per second), so the CPU arm times a bounded sample of the same
+    # per-track workload instead of the full 128 x 180 s batch: said here, not only in cpu_baseline.sample
+    cfg["timed_sample"] = sample
+    cfg["workload"] += f"; this arm times a bounded sample of it per step: {workers} tracks x {seconds:.0f} s"
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, world),
+        "config": cfg,
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": workers, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -250,6 +255,67 @@ def bind_to_gpu_numa(index: int):
         return f"numa node {node}, affinity unchanged"
     except Exception as exc:  # no sysfs entry, no NVML, restricted container ...
         return f"unbound ({type(exc).__name__})"
+
+
+def pcie_probe(dev, nbytes=1 << 30, reps=3):
+    """GB/s of pinned cudaMemcpyAsync over this GPU's link: host->device alone, device->host alone, both at once."""
+    import torch
+
+    h_up = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_dn = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d_up = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_dn = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+
+    def timed(up, down):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            if up:
+                with torch.cuda.stream(s1):
+                    d_up.copy_(h_up, non_blocking=True)
+            if down:
+                with torch.cuda.stream(s2):
+                    h_dn.copy_(d_dn, non_blocking=True)
+        torch.cuda.synchronize()
+        return reps * nbytes / (time.perf_counter() - t0) / 1e9
+
+    timed(True, True)  # first touch of the pinned pages
+    out = {"h2d_gbs": timed(True, False), "d2h_gbs": timed(False, True)}
+    both = timed(True, True)   # bytes per direction per second while both directions run
+    out["bidir_each_gbs"] = both
+    del h_up, h_dn, d_up, d_dn
+    torch.cuda.empty_cache()
+    return out
+
+
+def verify_one_track(plan, x, res):
+    """One track of the bench batch against the oracle at the parity tolerance (outside every timed region)."""
+    from oracle import frontend as ofe
+    from oracle import librosa_np as olr
+    from oracle import pyloudnorm_np as opl
+
+    mono = np.mean(x, axis=0)
+    mag = np.abs(olr.stft(mono, n_fft=N_FFT, hop_length=HOP))
+    ok = np.abs(res["magnitude"] - mag) <= 1e-6 + 1e-4 * mag
+    checks = {"magnitude": bool(ok.size - int(ok.sum()) <= max(1, int(1e-6 * ok.size)))}
+    mel = np.einsum("ft,mf->mt", mag**2, olr.filters_mel(SR, N_FFT, n_mels=N_MELS), optimize=True)
+    env = olr.onset_strength(S=olr.power_to_db(mel), sr=SR, hop_length=HOP)
+    close = lambda a, b: bool(np.allclose(a, b, rtol=1e-4, atol=1e-6))  # noqa: E731
+    checks["mel"] = close(res["mel"], mel)
+    checks["onset_env"] = close(res["onset_env"], env)
+    checks["autocorr"] = close(res["autocorr"], olr.autocorrelate(env))
+    checks["ltas"] = close(res["ltas"], np.mean(mag, axis=1))
+    checks["centroid"] = close(res["centroid"], olr.spectral_centroid(mono, SR, N_FFT, HOP)[0])
+    freqs = np.fft.rfftfreq(N_FFT, 1.0 / SR)
+    checks["rolloff_bins_equal"] = bool(np.mean(freqs[res["rolloff_bin"]] == olr.spectral_rolloff(mono, SR, N_FFT, HOP)[0]) >= 0.9995)
+    chroma, tuning = olr.chroma_stft(mono, SR, return_tuning=True)
+    checks["tuning"] = bool(abs(res["tuning"] - tuning) < 1e-12)
+    checks["chroma"] = close(res["chroma"], chroma)
+    checks["tempogram"] = close(res["tempogram"], olr.tempogram(onset_envelope=env, sr=SR, hop_length=HOP))
+    checks["lufs"] = bool(abs(res["lufs"] - opl.integrated_loudness(mono, SR)) < 0.01)
+    checks["mid_side_rms"] = close(np.sqrt(np.asarray([res["moments"][5], res["moments"][6]]) / res["moments"][7]), ofe.mid_side_rms(x))
+    return checks
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -328,11 +394,43 @@ def ours(args, rank, world, local_rank):
     ms_kernel_max = float(t.item())
     lufs = bufs.t["lufs"].cpu().numpy()
     assert np.all(np.isfinite(lufs)), "frontend produced non-finite loudness"
+    verified = None
+    if rank == 0 and not args.no_verify:
+        # one random track of the timed batch against the oracle, outside the timing (its first `verify_seconds`, so that the
+        # float64 oracle stays within seconds: the kernels are re-run on exactly that excerpt)
+        pick = int(np.random.default_rng(args.steps).integers(0, nt))
+        n_v = min(n, int(args.verify_seconds * SR))
+        x_v = host_pool[pick % pool_n].numpy().reshape(2, n)[:, :n_v].copy()
+        full = engine.download_track(batch, bufs, pick, ("magnitude", "mel"))
+        part = engine.analyse_batch(plan, [x_v], engine.FRONTEND_OUTPUTS)[0]
+        T_v = 1 + n_v // HOP
+        inner = T_v - 8   # frames whose windows end inside the excerpt see the same samples in the full-length run
+        same = bool(np.array_equal(full["magnitude"][:, :inner], part["magnitude"][:, :inner]) and
+                    np.array_equal(full["mel"][:, :inner], part["mel"][:, :inner]))
+        checks = verify_one_track(plan, x_v, part)
+        checks["batch_track_equals_excerpt_run"] = same
+        verified = {"ok": bool(all(checks.values())), "track": pick, "seconds": n_v / SR, "checks": checks}
 
     # ---- end-to-end leg ------------------------------------------------------------------
     chunk = min(args.chunk_tracks, nt)
     del bufs, batch, pcm
     torch.cuda.empty_cache()
+    pcie = None
+    if not args.no_pcie_probe:
+        # the link's own limits: this rank alone (ranks take turns), then every rank at once (what the host can feed)
+        alone = None
+        for r in range(world):
+            barrier()
+            if r == rank:
+                alone = pcie_probe(dev)
+        barrier()
+        together = pcie_probe(dev) if world > 1 else alone
+        barrier()
+        pcie = {"alone": alone, "all_ranks_together": together}
+        if world > 1:
+            agg = torch.tensor([together["bidir_each_gbs"]], dtype=torch.float64, device=dev)
+            dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+            pcie["all_ranks_together_sum_each_direction_gbs"] = float(agg.item())
     pipe = engine.HostPipeline(plan, n, 2, chunk, engine.FRONTEND_OUTPUTS)
     tracks = [host_pool[i % pool_n] for i in range(nt)]
     sink = []
@@ -432,11 +530,25 @@ def ours(args, rank, world, local_rank):
                          "algorithmic_bytes_per_launch": k1_bytes},
             "e2e": {"value": world * audio_per_step / s_e2e_max, "unit": UNIT,
                     "h2d_bytes_per_step": nt * 2 * n * 4, "d2h_bytes_per_step": d2h_full,
-                    "steps": e2e_steps, "s_per_step": s_e2e_max, "chunk_tracks": chunk},
+                    "steps": e2e_steps, "s_per_step": s_e2e_max, "chunk_tracks": chunk,
+                    "h2d_gbs_per_gpu": nt * 2 * n * 4 / s_e2e_max / 1e9, "d2h_gbs_per_gpu": d2h_full / s_e2e_max / 1e9},
             "gpu_launches": int(launches),
+            "verified": (verified or {}).get("ok"),
+            "verification": verified,
             "clocks": clk.summary(),
             "host_binding": numa_note,
         }
+        if pcie:
+            # the busier direction of the end-to-end leg against what the link moves in that direction while both run
+            # (all ranks together: the host's ceiling at N > 1)
+            lim = pcie.get("all_ranks_together_sum_each_direction_gbs", pcie["all_ranks_together"]["bidir_each_gbs"])
+            busy = world * max(line["e2e"]["h2d_gbs_per_gpu"], line["e2e"]["d2h_gbs_per_gpu"])
+            line["e2e"]["pcie"] = pcie
+            line["e2e"]["pcie_ceiling_gbs"] = lim
+            line["e2e"]["pcie_frac"] = busy / lim if lim else None
+            # per-GPU efficiency of the end-to-end leg against one GPU that has the host to itself
+            line["e2e"]["per_gpu_link_share"] = (pcie["all_ranks_together"]["bidir_each_gbs"] / pcie["alone"]["bidir_each_gbs"]
+                                                 if pcie["alone"] and pcie["alone"]["bidir_each_gbs"] else None)
         if e2e_analysis:
             line["e2e_analysis_outputs"] = e2e_analysis
         if cpu_baseline:
@@ -460,6 +572,9 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=60.0, help="track length of the bounded CPU sample (one track per worker)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-analysis-leg", action="store_true", help="skip the informational byte-reduced end-to-end leg")
+    ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of one track of the batch after the timed region")
+    ap.add_argument("--verify-seconds", type=float, default=30.0)
+    ap.add_argument("--no-pcie-probe", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -418,6 +418,24 @@ def download(batch: DeviceBatch, bufs: FrontendBuffers) -> list[TrackResult]:
     return out
 
 
+def download_track(batch: DeviceBatch, bufs: FrontendBuffers, i: int, keys: Iterable[str]) -> TrackResult:
+    """Host copy of a few outputs of ONE track of a resident batch (slices on the device first: the matrices of a large
+    batch are gigabytes).  Supports the (rows, T) matrices and the per-frame series."""
+    plan = batch.plan
+    rows = {"magnitude": plan.n_bins, "mel": plan.n_mels, "chroma": 12, "tempogram": plan.tempogram_win, "mfcc": N_MFCC}
+    T, ld, po = int(batch.n_frames[i]), int(batch.pitch[i]), int(batch.pitch_off[i])
+    r = TrackResult(n_samples=int(batch.n_samples[i]), n_frames=T, channels=batch.channels)
+    for k in keys:
+        t = bufs.t[k]
+        if k in rows:
+            r.data[k] = t[rows[k] * po: rows[k] * (po + ld)].cpu().numpy().reshape(rows[k], ld)[:, :T]
+        elif t.ndim == 1 and t.numel() == batch.total_pitch:
+            r.data[k] = t[po: po + T].cpu().numpy()
+        else:
+            raise KeyError(f"download_track handles the (rows, T) matrices and the per-frame series, not {k!r}")
+    return r
+
+
 def lazy_results(batch: DeviceBatch, bufs: FrontendBuffers) -> list[TrackResult]:
     """Results whose outputs are copied to the host on first access (the device buffers stay referenced)."""
     plan = batch.plan
@@ -506,29 +524,32 @@ def analyse_host(plan: Plan, tracks: Sequence[np.ndarray], outputs: Iterable[str
 
 
 class HostPipeline:
-    """Double-buffered host -> HBM -> host streaming of equal-length tracks.
+    """Multi-buffered host -> HBM -> host streaming of equal-length tracks.
 
     The public end-to-end path for large batches: per chunk of ``chunk_tracks``
     tracks it copies pinned host PCM to the device on a copy stream, runs the fused
     frontend on a compute stream and copies every requested output back into
     pinned host buffers on a third stream, so PCIe transfers in both directions
-    overlap the kernels of the neighbouring chunks.
+    overlap the kernels of the neighbouring chunks.  ``n_buffers`` (default 3) sets
+    of device / pinned buffers rotate, so the host only waits when it is a whole
+    buffer set ahead of the device.
     """
 
     def __init__(self, plan: Plan, n_samples: int, channels: int, chunk_tracks: int,
-                 outputs: Iterable[str] = ALL_OUTPUTS, pcm16: bool = False):
+                 outputs: Iterable[str] = ALL_OUTPUTS, pcm16: bool = False, n_buffers: int = 3):
         """``pcm16``: the host tracks are interleaved int16 PCM (what a 16-bit WAV file holds, n_samples * channels
         values each); they are copied as such -- half the PCIe bytes -- and converted to planar float32 by the decode
         kernel on the copy stream."""
         self.plan, self.n_samples, self.channels, self.chunk = plan, int(n_samples), int(channels), int(chunk_tracks)
         self.pcm16 = bool(pcm16)
+        self.nbuf = nb = max(2, int(n_buffers))
         dev = torch.device(f"cuda:{plan.device}")
-        self.dev_raw = ([torch.empty(self.chunk * channels * self.n_samples, dtype=torch.int16, device=dev) for _ in range(2)]
+        self.dev_raw = ([torch.empty(self.chunk * channels * self.n_samples, dtype=torch.int16, device=dev) for _ in range(nb)]
                         if self.pcm16 else None)
         self.stride = (channels * self.n_samples + 3) & ~3
         offsets = np.arange(self.chunk, dtype=np.int64) * self.stride
         ns = np.full(self.chunk, self.n_samples, dtype=np.int64)
-        self.dev_in = [torch.empty(self.chunk * self.stride, dtype=torch.float32, device=dev) for _ in range(2)]
+        self.dev_in = [torch.empty(self.chunk * self.stride, dtype=torch.float32, device=dev) for _ in range(nb)]
         self.batches = [DeviceBatch(plan, d, offsets, ns, channels) for d in self.dev_in]
         self.requested = tuple(outputs)
         self.bufs = [FrontendBuffers(b, outputs) for b in self.batches]
@@ -537,13 +558,14 @@ class HostPipeline:
         self.host_out = [{k: torch.empty(v.shape, dtype=v.dtype, pin_memory=True) for k, v in bf.t.items()
                           if k in self.requested} for bf in self.bufs]
         self.s_copy, self.s_comp, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
-        self.ev_h2d = [torch.cuda.Event() for _ in range(2)]
-        self.ev_comp = [torch.cuda.Event() for _ in range(2)]
-        self.ev_d2h = [torch.cuda.Event() for _ in range(2)]
+        self.ev_h2d = [torch.cuda.Event() for _ in range(nb)]
+        self.ev_comp = [torch.cuda.Event() for _ in range(nb)]
+        self.ev_d2h = [torch.cuda.Event() for _ in range(nb)]
         self.h2d_bytes_per_track = channels * self.n_samples * (2 if self.pcm16 else 4)
         self.d2h_bytes_per_chunk = sum(t.numel() * t.element_size() for t in self.host_out[0].values())
         # partial final chunks reuse the full-size buffers with a shorter batch view
         self._ws = workspace(plan, self.batches[0])
+        self._tails = []
 
     def run(self, host_tracks: Sequence[torch.Tensor], consume=None) -> int:
         """Process ``host_tracks`` (pinned 1-d float32 tensors of C*N samples each).
@@ -552,8 +574,9 @@ class HostPipeline:
         chunk's results are in pinned host memory.  Returns the number of chunks.
         """
         n = len(host_tracks)
+        nb = self.nbuf
         n_chunks = (n + self.chunk - 1) // self.chunk
-        pending = [None, None]
+        pending = [None] * nb
         cur = torch.cuda.current_stream()
         for s in (self.s_copy, self.s_comp, self.s_out):
             s.wait_stream(cur)
@@ -566,7 +589,7 @@ class HostPipeline:
                 pending[b] = None
 
         for ci in range(n_chunks):
-            b = ci & 1
+            b = ci % nb
             finish(b)  # the host has consumed buffer b's previous results
             first = ci * self.chunk
             cnt = min(self.chunk, n - first)
@@ -588,7 +611,7 @@ class HostPipeline:
                 batch = self.batches[b]
                 if cnt != self.chunk:
                     batch = DeviceBatch(self.plan, self.dev_in[b], batch.offsets[:cnt], batch.n_samples[:cnt], self.channels)
-                    self._tail = batch  # keep host metadata alive until the stream has consumed it
+                    self._tails.append(batch)  # keep host metadata alive until the stream has consumed it
                 run_device(self.plan, batch, self.bufs[b])
                 self.ev_comp[b].record(self.s_comp)
             with torch.cuda.stream(self.s_out):
@@ -597,7 +620,8 @@ class HostPipeline:
                     h.copy_(self.bufs[b].t[k], non_blocking=True)
                 self.ev_d2h[b].record(self.s_out)
             pending[b] = (ci, first, cnt)
-        finish(n_chunks & 1)
-        finish((n_chunks + 1) & 1)
+        for k in range(nb):   # drain in submission order
+            finish((n_chunks + k) % nb)
         cur.wait_stream(self.s_out)
+        self._tails.clear()
         return n_chunks

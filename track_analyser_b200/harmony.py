@@ -194,6 +194,8 @@ def harmony_frontend(audio: AudioInput) -> HarmonyFrontend:
 def _chroma_cqt(y: np.ndarray, sr: int) -> np.ndarray:
     """librosa.feature.chroma_cqt(y=y, sr=sr) -> (12, T) float32 (harmony.py:107,148), by the constant-Q kernels of
     ``csrc/cqt.cu``.  Raises like librosa does when the basis does not fit under the Nyquist frequency."""
+    if runtime.is_precomputed():
+        return runtime.frontend(np.asarray(y, dtype=np.float32), sr, outputs=("chroma_cqt",))["chroma_cqt"]
     plan = runtime.get_plan(sr)
     if not plan.cqt_ok:
         try:

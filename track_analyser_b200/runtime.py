@@ -106,6 +106,42 @@ def alias_mono_to_stereo(mono: np.ndarray, stereo: np.ndarray) -> bool:
     return True
 
 
+@contextlib.contextmanager
+def precomputed_session(results: dict):
+    """Scope in which every ``frontend()`` request is answered from ``results`` and nothing touches the GPU.
+
+    ``results``: ``{(n_fft, hop, n_mels, channels): TrackResult}`` of ONE track, produced by a batched run elsewhere
+    (``pipeline.analyse_tracks`` runs the kernels on whole chunks in the parent and the per-track host stages in worker
+    processes).  A request for the mono view of a stereo track falls back to the stereo entry when there is no mono one
+    (mono == mid exactly, utils.py:116).  Requests outside what was precomputed raise instead of computing."""
+    prev = getattr(_local, "precomputed", None)
+    _local.precomputed = results
+    try:
+        yield results
+    finally:
+        _local.precomputed = prev
+
+
+def is_precomputed() -> bool:
+    """True inside a ``precomputed_session`` (the caller must not create plans or touch the GPU)."""
+    return getattr(_local, "precomputed", None) is not None
+
+
+def _from_precomputed(pre: dict, x: np.ndarray, n_fft, hop, n_mels, roll_percent, meter_block, window, want):
+    if float(roll_percent) != 0.85 or float(meter_block) != 0.4 or window != "hann":
+        raise RuntimeError("precomputed session: only the default roll_percent / meter_block / window are available")
+    ch = 2 if (x.ndim == 2 and x.shape[0] == 2) else 1
+    hit = pre.get((int(n_fft), int(hop), int(n_mels), ch))
+    if hit is None and ch == 1:
+        hit = pre.get((int(n_fft), int(hop), int(n_mels), 2))
+    if hit is None:
+        raise RuntimeError(f"precomputed session: no result for n_fft={n_fft} hop={hop} n_mels={n_mels} channels={ch}")
+    missing = [o for o in (want or ()) if o not in hit]
+    if missing:
+        raise RuntimeError(f"precomputed session: outputs {missing} were not computed for n_fft={n_fft} hop={hop}")
+    return hit
+
+
 def _plan_outputs(plan: engine.Plan, n_mels: int, n_samples: int, outs) -> tuple:
     """Drop what this plan / track cannot produce from a requested output set."""
     outs = tuple(outs)
@@ -126,6 +162,9 @@ def frontend(samples: np.ndarray, sample_rate: int, *, n_fft: int = 2048, hop: i
         x = x[0]
     cache = getattr(_local, "cache", None)
     want = tuple(outputs) if outputs is not None else None
+    pre = getattr(_local, "precomputed", None)
+    if pre is not None:
+        return _from_precomputed(pre, x, n_fft, hop, n_mels, roll_percent, meter_block, window, want)
     plan = get_plan(sample_rate, n_fft, hop, n_mels, roll_percent=roll_percent, meter_block=meter_block, window=window)
     everything = tuple(o for o in engine.ALL_OUTPUTS if o != "cqt_mag")
     key = None
