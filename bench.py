@@ -488,6 +488,32 @@ def ours(args, rank, world, local_rank):
             del pipe_a
             torch.cuda.empty_cache()
 
+    # ---- informational: the batch API down to the reference's dataclasses (pipeline.analyse_tracks) ---------------------
+    e2e_track = None
+    if not args.no_analysis_leg and args.analysis_tracks > 0:
+        from track_analyser_b200 import pipeline
+        from track_analyser_b200.utils import AudioInput
+
+        pool_audio = []
+        for t_ in host_pool:
+            st = t_.numpy().reshape(2, n)
+            pool_audio.append(AudioInput(samples=np.mean(st, axis=0), sample_rate=SR, stereo_samples=st))
+        na = min(args.analysis_tracks, nt)
+        srcs = [pool_audio[i % pool_n] for i in range(na)]
+        pipeline.analyse_tracks(srcs[: min(na, 2 * args.chunk_tracks)], chunk_tracks=args.chunk_tracks)   # forks the workers, warms the plans
+        barrier()
+        t0 = time.perf_counter()
+        out = pipeline.analyse_tracks(srcs, chunk_tracks=args.chunk_tracks)
+        dt = time.perf_counter() - t0
+        ta = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        assert len(out) == na and all(90.0 <= o.beat.bpm <= 135.0 for o in out)
+        e2e_track = {"value": world * na * args.seconds / float(ta.item()), "unit": UNIT, "tracks_per_gpu": na,
+                     "s_total": float(ta.item()), "host_workers": pipeline._worker_count(None),
+                     "note": "pipeline.analyse_tracks: host AudioInput in -> TrackAnalysisResult dataclasses out (beats, structure, "
+                             "loudness, harmony incl. chroma_cqt, features, stereo); host stages in worker processes"}
+
     if rank == 0:
         B = N_FFT // 2 + 1
         T = 1 + n // HOP
@@ -551,6 +577,8 @@ def ours(args, rank, world, local_rank):
                                                  if pcie["alone"] and pcie["alone"]["bidir_each_gbs"] else None)
         if e2e_analysis:
             line["e2e_analysis_outputs"] = e2e_analysis
+        if e2e_track:
+            line["e2e_analyse_track"] = e2e_track
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
@@ -572,6 +600,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=60.0, help="track length of the bounded CPU sample (one track per worker)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-analysis-leg", action="store_true", help="skip the informational byte-reduced end-to-end leg")
+    ap.add_argument("--analysis-tracks", type=int, default=128, help="tracks per GPU of the pipeline.analyse_tracks leg (0: skip)")
     ap.add_argument("--no-verify", action="store_true", help="skip the oracle check of one track of the batch after the timed region")
     ap.add_argument("--verify-seconds", type=float, default=30.0)
     ap.add_argument("--no-pcie-probe", action="store_true")

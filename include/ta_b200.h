@@ -223,6 +223,12 @@ TA_API int ta_chroma_stft(const ta_plan* plan, const ta_batch* batch, const floa
 TA_API int ta_decode_pcm(const void* interleaved, int format, int channels, int64_t n_frames, float* planar_out,
                          void* stream);
 
+/* Is `mono` (n_samples floats) exactly the float32 mean of the planar pair `planar_stereo` (L then R, n_samples each), the
+ * way utils.coerce_audio builds AudioInput.samples from stereo_samples (utils.py:116)?  ORs 1 into *mismatch (device int32,
+ * zeroed by the caller) if any sample differs.  The batch driver uses it to decide whether one stereo run may serve the
+ * mono stages of a track too (mono == mid exactly); NaNs count as a mismatch. */
+TA_API int ta_mono_mix_check(const float* planar_stereo, const float* mono, int64_t n_samples, int32_t* mismatch, void* stream);
+
 /* K9: per-frame sums of the harmonic and percussive components of librosa.decompose.hpss (31-wide median
  * filters along time and frequency, soft masks with power 2) on an existing magnitude spectrogram:
  * analysis/structure.py:52 as consumed at :143-144 and :212-213.  scratch: B * P floats. */

@@ -27,7 +27,30 @@ __global__ void __launch_bounds__(256) decode_pcm_kernel(const unsigned char* __
         for (int c = 0; c < channels; ++c) dst[(size_t)c * n_frames + f] = pcm_sample<FMT>(src, size_t(f) * channels + c);
 }
 
+// mismatch |= any((L[i] + R[i]) * 0.5f != mono[i]): is `mono` exactly the float32 mean of the planar pair (utils.py:116)?
+__global__ void __launch_bounds__(256) mono_mix_check_kernel(const float* __restrict__ left, const float* __restrict__ right,
+                                                            const float* __restrict__ mono, long long n, int* __restrict__ mismatch) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    bool bad = false;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        bad |= !(__fmul_rn(__fadd_rn(left[i], right[i]), 0.5f) == mono[i]);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(mismatch, 1);
+}
+
 }  // namespace ta
+
+extern "C" int ta_mono_mix_check(const float* planar_stereo, const float* mono, int64_t n_samples, int32_t* mismatch, void* stream) {
+    using namespace ta;
+    TA_REQUIRE(planar_stereo && mono && mismatch, "pointers must not be NULL");
+    TA_REQUIRE(n_samples >= 0, "n_samples must be >= 0");
+    if (n_samples == 0) return TA_OK;
+    const int grid = int(std::min<long long>((n_samples + 255) / 256, 148 * 8));
+    mono_mix_check_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(planar_stereo, planar_stereo + n_samples, mono,
+                                                                                   n_samples, mismatch);
+    count_launch();
+    TA_CUDA(cudaGetLastError());
+    return TA_OK;
+}
 
 extern "C" int ta_decode_pcm(const void* interleaved, int format, int channels, int64_t n_frames, float* planar_out,
                              void* stream) {

@@ -84,8 +84,25 @@ def analyse_track(source, *, output_dir: Optional[str | Path] = None, use_stems:
 # ---------------------------------------------------------------------------------------------------------------------
 _PLAN_A = (2048, 512, 128)   # the default plan of beats / structure / loudness / harmony / features / stereo
 _PLAN_B = (4096, 1024, 0)    # harmony._spectral_balance (harmony.py:253-267)
+_ring = None
 _pool = None
 _pool_size = 0
+
+
+def _shutdown():
+    """Stop the worker processes and drop the shared-memory ring (also registered with atexit)."""
+    global _pool, _ring
+    if _pool is not None:
+        _pool.shutdown(wait=True, cancel_futures=True)
+        _pool = None
+    if _ring is not None:
+        _ring.close()
+        _ring = None
+
+
+import atexit  # noqa: E402
+
+atexit.register(_shutdown)
 
 
 def _worker_count(workers: Optional[int]) -> int:
@@ -107,8 +124,16 @@ def _get_pool(n: int):
         import concurrent.futures as cf
         import multiprocessing as mp
 
-        _pool = cf.ProcessPoolExecutor(max_workers=n, mp_context=mp.get_context("fork"))
+        # everything the stages import lazily is loaded here once, so that the forked children inherit it
+        import pandas  # noqa: F401
+        import scipy.fft  # noqa: F401
+        import scipy.ndimage  # noqa: F401
+        import scipy.signal  # noqa: F401
+
+        _pool = cf.ProcessPoolExecutor(max_workers=n, mp_context=mp.get_context("fork"), initializer=_worker_init)
         _pool_size = n
+        # the executor forks its workers on demand: make it fork all of them now, outside anybody's timed region
+        list(_pool.map(_worker_warm, [0.05] * (4 * n), chunksize=1))
     return _pool
 
 
@@ -120,33 +145,67 @@ def _placeholder_audio(meta: dict) -> AudioInput:
     return AudioInput(samples, meta["sample_rate"], meta["path"], stereo_)
 
 
-def _load_results(path: str, layout: dict) -> dict:
-    """{plan key: TrackResult} from the chunk's shared-memory file: zero-copy views of what the parent wrote."""
-    from .engine import TrackResult
+def _load_results(path: str, base: int, specs: dict, index: int) -> dict:
+    """{plan key: TrackResult} of track ``index`` of a chunk from the chunk's shared-memory file: the parent wrote every
+    output array of the batch there once; the per-track pieces are views cut out of the mapping (``engine._cut``)."""
+    from . import engine
 
     buf = np.memmap(path, dtype=np.uint8, mode="r")
     out = {}
-    for key, entry in layout.items():
-        r = TrackResult(n_samples=entry["n_samples"], n_frames=entry["n_frames"], channels=entry["channels"])
-        for name, (off, shape, dtype, scalar) in entry["arrays"].items():
-            a = np.ndarray(shape, dtype=dtype, buffer=buf, offset=off)
-            r.data[name] = a.reshape(()).item() if scalar else a
+    for key, (plan_g, batch_g, arrays) in specs.items():
+        r = engine.TrackResult(n_samples=int(batch_g.n_samples[index]), n_frames=int(batch_g.n_frames[index]),
+                               channels=batch_g.channels)
+        for name, (off, shape, dtype) in arrays.items():
+            h = np.ndarray(shape, dtype=dtype, buffer=buf, offset=base + off)
+            r.data[name] = engine._cut(plan_g, batch_g, index, name, h)
         out[key] = r
     return out
 
 
+def _worker_init():
+    """The host stages are many small numpy / scipy calls: one BLAS / OpenMP thread per worker, or a dozen workers' thread
+    pools fight over the same cores."""
+    try:
+        import threadpoolctl
+
+        threadpoolctl.threadpool_limits(1)
+    except Exception:  # pragma: no cover - best effort
+        pass
+    try:
+        import torch
+
+        torch.set_num_threads(1)
+    except Exception:  # pragma: no cover
+        pass
+
+
+def _worker_warm(seconds: float) -> int:
+    import time
+
+    time.sleep(seconds)
+    return os.getpid()
+
+
 def _stage_worker(task):
     """Worker process: the host stages of one track on precomputed frontend results."""
-    path, layout, meta, seed = task
-    results = _load_results(path, layout)
+    import time
+
+    t0 = time.perf_counter()
+    path, base, specs, index, meta, seed = task
+    results = _load_results(path, base, specs, index)
     audio = _placeholder_audio(meta)
     with runtime.precomputed_session(results):
-        return _run_stages(audio, seed, lambda stage: None)
+        stages = _run_stages(audio, seed, lambda stage: None)
+    if os.environ.get("TA_TRACE_WORKERS"):
+        import sys
+
+        print(f"[ta worker {os.getpid()}] {(time.perf_counter() - t0) * 1e3:.1f} ms", file=sys.stderr)
+    return stages
 
 
-def _stereo_buffer(audio: AudioInput):
-    """(buffer for the batched run, channels, aliased) -- the planar stereo pair when the mono samples are exactly its
-    mean (one run then serves the mono stages too), else None: such a track goes through ``analyse_track``."""
+def _batch_buffer(audio: AudioInput):
+    """(buffer for the batched run, channels) from the shapes and dtypes alone: the planar float32 stereo pair, or the mono
+    samples of a track without one; None for layouts the batched path does not take."""
     st = audio.stereo_samples
     mono = np.asarray(audio.samples)
     if mono.dtype != np.float32 or mono.ndim != 1:
@@ -156,10 +215,50 @@ def _stereo_buffer(audio: AudioInput):
     st = np.asarray(st)
     if st.dtype != np.float32 or st.ndim != 2 or st.shape[0] != 2 or st.shape[1] != mono.shape[0] or not st.flags.c_contiguous:
         return None
-    with runtime.frontend_session():
-        if not runtime.alias_mono_to_stereo(mono, st):
-            return None
     return st, 2
+
+
+class _ShmRing:
+    """A few slots of one /dev/shm file, registered with the CUDA driver as pinned memory: the parent copies a chunk's output
+    arrays device -> slot at link speed, the workers map the same file and read the slot.  Slots are reused, so their pages
+    are touched (and pinned) once, not per chunk."""
+
+    def __init__(self, slots: int = 4):
+        import tempfile
+
+        shm_dir = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+        fd, self.path = tempfile.mkstemp(prefix="ta_b200_", dir=shm_dir)
+        os.close(fd)
+        self.slots, self.slot_bytes, self.mm, self._registered = slots, 0, None, None
+
+    def _unregister(self):
+        if self._registered is not None:
+            import torch
+
+            torch.cuda.cudart().cudaHostUnregister(self._registered)
+            self._registered = None
+
+    def ensure(self, slot_bytes: int):
+        """Grow the file so that every slot holds ``slot_bytes`` (only when no slot is in use)."""
+        if slot_bytes <= self.slot_bytes:
+            return
+        import torch
+
+        self._unregister()
+        self.slot_bytes = (max(slot_bytes, 1 << 20) * 5 // 4 + 4095) & ~4095
+        self.mm = np.memmap(self.path, dtype=np.uint8, mode="w+", shape=(self.slots * self.slot_bytes,))
+        self.mm[:: 4096] = 0   # touch every page once
+        ptr = self.mm.ctypes.data
+        if int(torch.cuda.cudart().cudaHostRegister(ptr, self.mm.nbytes, 0)) == 0:
+            self._registered = ptr
+
+    def close(self):
+        self._unregister()
+        self.mm = None
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
 
 
 def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] = None, chunk_tracks: int = 8,
@@ -168,86 +267,171 @@ def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] 
     tracks (two fused runs per chunk: the 2048/512 plan with every output the host stages consume, the 4096/1024 plan of the
     spectral balance on the same resident PCM) while a pool of ``workers`` processes (default: all cores but one;
     0 = in this process) runs the beat / structure / loudness / harmony / feature / stereo host logic of earlier chunks on
-    the downloaded arrays.  Mirrors pipeline.py:32-120 per track; results equal ``analyse_track``'s."""
-    import tempfile
+    the downloaded arrays.  Three things overlap: a thread verifies and uploads the next chunk, this thread runs the
+    kernels and copies their outputs into a pinned shared-memory ring, the workers run the host stages.  Mirrors
+    pipeline.py:32-120 per track; results equal ``analyse_track``'s."""
+    import concurrent.futures as cf
+    import queue
+    import sys
+    import threading
+    import time
 
+    import ctypes as C
+
+    import torch
+
+    from . import _native as nat
     from . import engine
 
-    import concurrent.futures as cf
-
+    global _ring
+    trace = bool(os.environ.get("TA_TRACE_WORKERS"))
     audios = [s if isinstance(s, AudioInput) else coerce_audio(s) for s in sources]
     results: list = [None] * len(audios)
-    groups: dict = {}
-    # mono == mean(stereo) is verified sample for sample before one stereo run may serve both views: numpy releases the
-    # GIL in these passes, so a few threads do it for all tracks at once
-    with cf.ThreadPoolExecutor(max_workers=min(8, max(1, len(audios)))) as tp:
-        checked = list(tp.map(_stereo_buffer, audios))
-    for i, a in enumerate(audios):
-        buf = checked[i]
-        if buf is None or buf[0].shape[-1] == 0:
-            results[i] = analyse_track(a, seed=seed)   # layouts the batched path does not take
-            continue
-        groups.setdefault((int(a.sample_rate), buf[1]), []).append((i, buf[0]))
+    if not audios:
+        return results
     n_workers = _worker_count(workers)
-    pool = _get_pool(n_workers) if n_workers > 0 else None
-    shm_dir = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
-    pending = []   # (futures, indices, path)
+    pool = _get_pool(n_workers) if n_workers > 0 else None   # forked before this call starts any thread of its own
+    dev_index = torch.cuda.current_device() if device is None else int(device)
+    main_stream = torch.cuda.current_stream(dev_index)
+
+    # group by (sample rate, channel layout) from the shapes alone; whether a stereo pair may serve the mono view too
+    # (mono == mean(stereo), sample for sample) is verified by the uploader thread chunk by chunk
+    groups: dict = {}
+    for i, a in enumerate(audios):
+        st = a.stereo_samples
+        ch = 2 if (st is not None and np.ndim(st) == 2 and np.shape(st)[0] == 2) else (1 if st is None else 0)
+        groups.setdefault((int(a.sample_rate), ch), []).append(i)
+    chunks = []
+    for (sr, ch), idxs in groups.items():
+        if ch == 0:   # layouts the batched path does not take ((1, N) / (N, 2) stereo_samples ...)
+            for i in idxs:
+                results[i] = analyse_track(audios[i], seed=seed)
+            continue
+        chunks += [(sr, ch, idxs[c0: c0 + chunk_tracks]) for c0 in range(0, len(idxs), chunk_tracks)]
+
+    uploaded: "queue.Queue" = queue.Queue(maxsize=2)
+
+    def uploader():
+        try:
+            stream = torch.cuda.Stream(dev_index)
+            with torch.cuda.stream(stream):
+                for sr, ch, idxs in chunks:
+                    cand, bad = [], []
+                    for i in idxs:
+                        c = _batch_buffer(audios[i])
+                        (cand if (c is not None and c[1] == ch and c[0].shape[-1] > 0) else bad).append((i, c))
+                    batch, good = None, []
+                    if cand:
+                        plan_a = runtime.get_plan(sr, *_PLAN_A, device=device)
+                        batch = engine.upload(plan_a, [c[0] for _, c in cand])
+                        ok = [True] * len(cand)
+                        if ch == 2:
+                            # one stereo run may serve the mono stages only if mono == mean(stereo) sample for sample
+                            # (utils.py:116): checked on the device, next to the PCM that is there anyway
+                            monos = engine.upload(plan_a, [np.asarray(audios[i].samples, dtype=np.float32) for i, _ in cand])
+                            flags = torch.zeros(len(cand), dtype=torch.int32, device=batch.pcm.device)
+                            st_ptr = C.c_void_p(torch.cuda.current_stream(dev_index).cuda_stream)
+                            for j in range(len(cand)):
+                                nat.check(plan_a.lib.ta_mono_mix_check(
+                                    C.c_void_p(batch.pcm.data_ptr() + 4 * int(batch.offsets[j])),
+                                    C.c_void_p(monos.pcm.data_ptr() + 4 * int(monos.offsets[j])), int(batch.n_samples[j]),
+                                    C.c_void_p(flags.data_ptr() + 4 * j), st_ptr))
+                            ok = [v == 0 for v in flags.cpu().tolist()]
+                            del monos
+                        if not all(ok):   # rare: re-upload only the consistent tracks, the others take the single-track path
+                            bad += [ic for ic, o in zip(cand, ok) if not o]
+                            cand = [ic for ic, o in zip(cand, ok) if o]
+                            batch = engine.upload(plan_a, [c[0] for _, c in cand]) if cand else None
+                        good = [(i, c[0]) for i, c in cand]
+                        if batch is not None:
+                            batch.pcm.record_stream(main_stream)
+                    bad = [i for i, _ in bad]
+                    uploaded.put((sr, ch, good, bad, batch))
+            uploaded.put(None)
+        except BaseException as exc:  # noqa: BLE001 - handed to the consuming thread
+            uploaded.put(exc)
+
+    th = threading.Thread(target=uploader, daemon=True)
+    th.start()
+    if _ring is None:
+        _ring = _ShmRing()
+    ring, pending = _ring, []   # pending: (futures, indices, slot)
+    free_slots = list(range(ring.slots))
 
     def collect(entry):
-        futs, idxs, path = entry
+        futs, idxs, slot = entry
         for i, f in zip(idxs, futs):
             stages = f.result() if hasattr(f, "result") else f
             results[i] = TrackAnalysisResult(audio=audios[i], stems=None, **stages)
-        try:
-            os.unlink(path)
-        except OSError:
-            pass
+        free_slots.append(slot)
 
-    for (sr, channels), items in groups.items():
+    while True:
+        _t = [time.perf_counter()]
+        item = uploaded.get()
+        if item is None:
+            break
+        if isinstance(item, BaseException):
+            raise item
+        sr, channels, good, bad, batch = item
+        for i in bad:
+            results[i] = analyse_track(audios[i], seed=seed)   # e.g. mono samples that are not the mean of the stereo pair
+        if not good:
+            continue
+        _t.append(time.perf_counter())
         plan_a = runtime.get_plan(sr, *_PLAN_A, device=device)
         plan_b = runtime.get_plan(sr, *_PLAN_B, device=device)
+        tracks = [b for _, b in good]
         outs_a = engine.available_outputs(plan_a, engine.ANALYSIS_OUTPUTS)
-        for c0 in range(0, len(items), chunk_tracks):
-            chunk = items[c0: c0 + chunk_tracks]
-            tracks = [b for _, b in chunk]
-            batch = engine.upload(plan_a, tracks)
-            long_enough = all(t.shape[-1] >= plan_a.meter_block * sr for t in tracks)
-            oa = outs_a if long_enough else tuple(o for o in outs_a if o not in ("kw_blocks", "lufs"))
-            res_a = engine.analyse_batch(plan_a, tracks, oa, resident=batch)
-            res_b = engine.analyse_batch(plan_b, tracks, ("ltas",), resident=batch)
+        if not all(t.shape[-1] >= plan_a.meter_block * sr for t in tracks):
+            outs_a = tuple(o for o in outs_a if o not in ("kw_blocks", "lufs"))
+        runs = [((*_PLAN_A, channels), plan_a, batch, outs_a), ((*_PLAN_B, channels), plan_b, batch.rebind(plan_b), ("ltas",))]
+        if channels == 1:
             # a mono track's stereo stage analyses the duplicated channel pair (stereo.py:42-59): its own small run
-            res_d = (engine.analyse_batch(plan_a, [np.vstack([t, t]) for t in tracks], ("moments", "band_energy"))
-                     if channels == 1 else [None] * len(tracks))
-            # one shared-memory file per chunk: the workers map it instead of receiving pickled arrays
-            fd, path = tempfile.mkstemp(prefix="ta_b200_", dir=shm_dir)
-            os.close(fd)
-            layouts, cur, blobs = [], 0, []
-            for ra, rb, rd in zip(res_a, res_b, res_d):
-                layout = {}
-                for key, r in (((*_PLAN_A, channels), ra), ((*_PLAN_B, channels), rb)) + ((((*_PLAN_A, 2), rd),) if rd is not None else ()):
-                    arrays = {}
-                    for name, v in r.data.items():
-                        a = np.ascontiguousarray(v)
-                        arrays[name] = (cur, a.shape, a.dtype.str, not isinstance(v, np.ndarray))
-                        blobs.append((cur, a))
-                        cur += (a.nbytes + 63) & ~63
-                    layout[key] = dict(n_samples=r.n_samples, n_frames=r.n_frames, channels=r.channels, arrays=arrays)
-                layouts.append(layout)
-            mm = np.memmap(path, dtype=np.uint8, mode="w+", shape=(max(cur, 64),))
-            for off, a in blobs:
-                mm[off: off + a.nbytes] = a.reshape(-1).view(np.uint8)
-            mm.flush()
-            del mm
-            tasks = []
-            for (i, _), layout in zip(chunk, layouts):
-                a = audios[i]
-                meta = dict(sample_rate=a.sample_rate, path=a.path, mono_shape=np.asarray(a.samples).shape,
-                            stereo_shape=None if a.stereo_samples is None else np.asarray(a.stereo_samples).shape)
-                tasks.append((path, layout, meta, seed))
-            futs = [pool.submit(_stage_worker, t) for t in tasks] if pool is not None else [_stage_worker(t) for t in tasks]
-            pending.append((futs, [i for i, _ in chunk], path))
-            while len(pending) > 2:   # keep the device at most two chunks ahead of the host stages
+            runs.append(((*_PLAN_A, 2), plan_a, engine.upload(plan_a, [np.vstack([t, t]) for t in tracks]),
+                         ("moments", "band_energy")))
+        launched = []
+        for key, plan, bt, outs in runs:
+            bufs = engine.FrontendBuffers(bt, outs)
+            engine.run_device(plan, bt, bufs)
+            launched.append((key, plan, bt, bufs))
+        # every requested output array of the batch goes to one slot of the shared-memory ring with one copy each; the
+        # workers cut their track's views out of the mapping instead of receiving pickled arrays
+        specs, cur = {}, 0
+        for key, plan, bt, bufs in launched:
+            arrays = {}
+            for name in bufs.requested:
+                t = bufs.t[name]
+                arrays[name] = (cur, tuple(t.shape), np.dtype(str(t.dtype).replace("torch.", "")).str)
+                cur += (t.numel() * t.element_size() + 63) & ~63
+            specs[key] = (plan.geometry(), bt.geometry(with_cqt="chroma_cqt" in bufs.requested), arrays)
+        if cur > ring.slot_bytes:
+            while pending:   # nobody may be reading the file while it is re-created
                 collect(pending.pop(0))
+            ring.ensure(cur)
+        while not free_slots:
+            collect(pending.pop(0))
+        slot = free_slots.pop(0)
+        base = slot * ring.slot_bytes
+        for key, plan, bt, bufs in launched:
+            for name, (off, shape, dtype) in specs[key][2].items():
+                dst = np.ndarray(shape, dtype=dtype, buffer=ring.mm, offset=base + off)
+                torch.from_numpy(dst).copy_(bufs.t[name], non_blocking=True)
+        main_stream.synchronize()
+        del launched, batch
+        _t.append(time.perf_counter())
+        tasks = []
+        for j, (i, _) in enumerate(good):
+            a = audios[i]
+            meta = dict(sample_rate=a.sample_rate, path=a.path, mono_shape=np.asarray(a.samples).shape,
+                        stereo_shape=None if a.stereo_samples is None else np.asarray(a.stereo_samples).shape)
+            tasks.append((ring.path, base, specs, j, meta, seed))
+        futs = [pool.submit(_stage_worker, t) for t in tasks] if pool is not None else [_stage_worker(t) for t in tasks]
+        pending.append((futs, [i for i, _ in good], slot))
+        _t.append(time.perf_counter())
+        if trace:
+            print("[ta analyse_tracks] chunk of %d: wait for upload %.1f, kernels + copy to shm %.1f, submit %.1f ms"
+                  % ((len(good),) + tuple(1e3 * (b - a) for a, b in zip(_t, _t[1:]))), file=sys.stderr)
     for entry in pending:
         collect(entry)
+    th.join()
     return results
