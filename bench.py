@@ -324,9 +324,14 @@ def ours(args, rank, world, local_rank):
     workers = cpu_workers(world)
     # 1. host pool of distinct synthetic tracks (and, on rank 0 at N=1, the CPU baseline) BEFORE CUDA init: fork-safe
     pool_n = min(args.pool, args.tracks_per_gpu)
+    # this rank's tracks of the global batch, by the product's own partition rule (contiguous blocks for equal lengths)
+    from track_analyser_b200 import sharding
+
+    mine = sharding.partition([int(args.seconds * SR)] * (args.tracks_per_gpu * world), world)[rank]
+    assert len(mine) == args.tracks_per_gpu
     ctx = mp.get_context("fork")
     with ctx.Pool(min(workers, pool_n)) as pool:
-        host_np = pool.map(_gen_track, [(13_370 + rank * args.tracks_per_gpu + i, args.seconds) for i in range(pool_n)])
+        host_np = pool.map(_gen_track, [(13_370 + mine[i], args.seconds) for i in range(pool_n)])
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         audio, wall = run_cpu_sample(workers, args.ref_seconds)
