@@ -12,7 +12,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libta_b200.so")
+# TA_B200_LIB: another build of the same library (A/B timing of kernel variants); the default is the in-tree build
+LIB_PATH = os.environ.get("TA_B200_LIB") or os.path.join(_HERE, "libta_b200.so")
 
 TA_ABI_VERSION = 4
 TA_OK = 0

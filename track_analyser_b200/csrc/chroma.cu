@@ -16,12 +16,33 @@
 // The projection is HBM-bound (reads the magnitude once, 4*B*T bytes per track, 13 flop per
 // element) on CUDA cores; a tcgen05 version cannot beat an HBM-bound kernel and TF32 would
 // break the 1e-4 parity bar (DESIGN.md section "filterbank contraction").
+#include <cuda.h>
+
 #include <algorithm>
+#include <cstdlib>
+#include <mutex>
 
 #include "common.cuh"
 #include "fft2_core.cuh"
 
 namespace ta {
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* sym = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(sym);
+    });
+    return fn;
+}
 
 struct PeakList {
     float* mag;            // [cap_total]
@@ -205,38 +226,77 @@ __global__ void __launch_bounds__(256) chroma_fb_kernel(const double* __restrict
 // numpy evaluates it -- `total = np.cumsum(S, axis=-2)` is a SEQUENTIAL float32 chain per frame, the threshold is
 // float32(roll_percent) * total[-1], the answer the first bin whose running sum is not below it.  An integer decision,
 // so the chain is walked in numpy's order on the very float32 magnitudes K1 wrote: one extra FADD per bin and frame here
-// (hidden: the kernel is HBM-bound), a checkpoint of the running sum every ROLL_BLOCK bins in shared memory, and once
-// the total is known a second walk of at most ROLL_BLOCK bins from the last checkpoint below the threshold.
+// (hidden: the kernel is HBM-bound); see RollState below for how the answer is found without a second pass.
 #ifndef CP_ROWS
 #define CP_ROWS 8  // magnitude rows whose loads are in flight per thread
 #endif
+
+// Roll-off state of one thread's two frames.  K1 hands over sum_f |X| per frame, evaluated in another order (float32 chunk
+// sums combined in double): within ~7e-5 of numpy's sequential float32 total in the worst case.  While the projection walks
+// down the bins it keeps, per frame, the first bin whose running sum reaches (1 - ROLL_MARGIN) of the threshold that
+// estimate predicts, and the running sum just before it; once the exact total is known the answer is found by walking on
+// from there, typically zero to two bins.  If the exact threshold turns out below the margin (never observed; the bound
+// above excludes it) the walk restarts at bin 0, so the result is numpy's in every case.
+static constexpr float ROLL_MARGIN = 2e-4f;
+struct RollState {
+    float2 run, lo, before;   // running sums, early thresholds, running sum before the candidate bin
+    int kx, ky;               // candidate bins (-1: none yet)
+};
+__device__ __forceinline__ void roll_init(RollState& r, const float* frame_sum, size_t col, bool ok, bool ok1, float roll_percent) {
+    r.run = r.before = make_float2(0.f, 0.f);
+    const float s0 = ok ? frame_sum[col] : 0.f, s1 = ok1 ? frame_sum[col + 1] : 0.f;
+    r.lo = make_float2(roll_percent * s0 * (1.0f - ROLL_MARGIN), roll_percent * s1 * (1.0f - ROLL_MARGIN));
+    r.kx = r.ky = -1;
+}
+__device__ __forceinline__ void roll_step(RollState& r, const float2 m, int k) {
+    const float2 prev = r.run;
+    r.run.x = __fadd_rn(r.run.x, m.x);
+    r.run.y = __fadd_rn(r.run.y, m.y);
+    if (r.kx < 0 && !(r.run.x < r.lo.x)) { r.kx = k; r.before.x = prev.x; }
+    if (r.ky < 0 && !(r.run.y < r.lo.y)) { r.ky = k; r.before.y = prev.y; }
+}
+// first bin whose sequential float32 running sum is not below float32(roll_percent) * total, for frame column `colh`
+__device__ __forceinline__ int roll_finish(const float* __restrict__ colh, int ld, int n_bins, float roll_percent, float total,
+                                           float lo, int kc, float before) {
+    const float thr = __fmul_rn(roll_percent, total);
+    if (kc < 0 || thr < lo) { kc = 0; before = 0.f; }   // estimate too high: walk from the first bin
+    float r = before;
+    for (int k0 = kc; k0 < n_bins; k0 += 4) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = __ldg(colh + size_t(min(k0 + u, n_bins - 1)) * ld);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            r = __fadd_rn(r, v[u]);
+            if (k0 + u >= n_bins - 1 || !(r < thr)) return min(k0 + u, n_bins - 1);
+        }
+    }
+    return n_bins - 1;
+}
 static constexpr int CP_THREADS = 256;
-static constexpr int ROLL_BLOCK = 128;
-static_assert(ROLL_BLOCK % CP_ROWS == 0, "checkpoints fall on row-group boundaries");
+
 
 template <bool CHROMA, bool ROLL>
 __global__ void __launch_bounds__(CP_THREADS, 3) chroma_project_kernel(const TrackDesc* __restrict__ tracks,
                                                                        const float* __restrict__ mag, const float* __restrict__ fb,
                                                                        float* __restrict__ out, int32_t* __restrict__ rolloff_bin,
-                                                                       float roll_percent, int n_bins) {
+                                                                       const float* __restrict__ frame_sum, float roll_percent,
+                                                                       int n_bins) {
     using namespace p2;
-    extern __shared__ __align__(16) float wsm[];  // CHROMA: [n_bins * 12] filterbank; ROLL: then [n_ck][2 * CP_THREADS] checkpoints
+    extern __shared__ __align__(16) float wsm[];  // CHROMA: [n_bins * 12] filterbank
     const TrackDesc td = tracks[blockIdx.y];
     if (blockIdx.x * CP_THREADS * 2 >= td.n_frames) return;
     const int t = (blockIdx.x * CP_THREADS + threadIdx.x) * 2;
     const bool ok = t < td.n_frames;  // rows are padded to a multiple of 32 frames, so t, t+1 stay inside the row
     const float* __restrict__ col = mag + size_t(td.pitch_off) * n_bins + (ok ? t : 0);
     const float* __restrict__ w = fb + size_t(blockIdx.y) * n_bins * 12;
-    float2* ck = reinterpret_cast<float2*>(wsm + (CHROMA ? n_bins * 12 : 0)) + threadIdx.x;  // [block * CP_THREADS]
     float2 acc[12];
 #pragma unroll
     for (int c = 0; c < 12; ++c) acc[c] = make_float2(0.f, 0.f);
-    float2 run = make_float2(0.f, 0.f);   // sequential float32 running sums of the two frames
-    auto accumulate = [&](const float2 m, const float* wk) {
-        if (ROLL) {
-            run.x = __fadd_rn(run.x, m.x);
-            run.y = __fadd_rn(run.y, m.y);
-        }
+    RollState rs;
+    if (ROLL) roll_init(rs, frame_sum, size_t(td.pitch_off) + t, ok, ok && t + 1 < td.n_frames, roll_percent);
+    auto accumulate = [&](const float2 m, const float* wk, int k) {
+        if (ROLL) roll_step(rs, m, k);
         if (CHROMA) {
             const float2 s = pmul(m, m);
             const float4 w0 = *reinterpret_cast<const float4*>(wk);
@@ -253,46 +313,139 @@ __global__ void __launch_bounds__(CP_THREADS, 3) chroma_project_kernel(const Tra
     }
     int kk = 0;
     for (; kk + CP_ROWS <= n_bins; kk += CP_ROWS) {
-        if (ROLL && kk % ROLL_BLOCK == 0) ck[(kk / ROLL_BLOCK) * CP_THREADS] = run;  // sum of bins [0, kk)
         float2 m[CP_ROWS];
 #pragma unroll
         for (int u = 0; u < CP_ROWS; ++u) m[u] = __ldg(reinterpret_cast<const float2*>(col + size_t(kk + u) * td.ld));
 #pragma unroll
-        for (int u = 0; u < CP_ROWS; ++u) accumulate(m[u], wsm + (kk + u) * 12);
+        for (int u = 0; u < CP_ROWS; ++u) accumulate(m[u], wsm + (kk + u) * 12, kk + u);
     }
-    for (; kk < n_bins; ++kk) {
-        if (ROLL && kk % ROLL_BLOCK == 0) ck[(kk / ROLL_BLOCK) * CP_THREADS] = run;
-        accumulate(__ldg(reinterpret_cast<const float2*>(col + size_t(kk) * td.ld)), wsm + kk * 12);
-    }
+    for (; kk < n_bins; ++kk) accumulate(__ldg(reinterpret_cast<const float2*>(col + size_t(kk) * td.ld)), wsm + kk * 12, kk);
     if (!ok) return;
     if (ROLL) {
-        const int n_ck = (n_bins + ROLL_BLOCK - 1) / ROLL_BLOCK;
+        rolloff_bin[td.pitch_off + t] = roll_finish(col, td.ld, n_bins, roll_percent, rs.run.x, rs.lo.x, rs.kx, rs.before.x);
+        if (t + 1 < td.n_frames)
+            rolloff_bin[td.pitch_off + t + 1] = roll_finish(col + 1, td.ld, n_bins, roll_percent, rs.run.y, rs.lo.y, rs.ky, rs.before.y);
+    }
+    if (CHROMA) {
+        float2 mx = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            if (t + h >= td.n_frames) break;
-            const float thr = __fmul_rn(roll_percent, h ? run.y : run.x);
-            int b = 0;   // last checkpoint still below the threshold (running sums of non-negative values never decrease)
-            for (int j = 1; j < n_ck; ++j) {
-                const float2 c = ck[j * CP_THREADS];
-                if ((h ? c.y : c.x) < thr) b = j;
-            }
-            const float2 c0 = ck[b * CP_THREADS];
-            float r = h ? c0.y : c0.x;
-            int first = n_bins - 1;
-            const float* __restrict__ colh = col + h;
-            // second walk, 16 rows in flight (reading a few rows past the answer is harmless; the adds stay sequential)
-            for (int k0 = b * ROLL_BLOCK; k0 < n_bins && first == n_bins - 1; k0 += 16) {
-                float v[16];
-#pragma unroll
-                for (int u = 0; u < 16; ++u) v[u] = __ldg(colh + size_t(min(k0 + u, n_bins - 1)) * td.ld);
-#pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    r = __fadd_rn(r, v[u]);
-                    if (first == n_bins - 1 && k0 + u < n_bins - 1 && !(r < thr)) first = k0 + u;
-                }
-            }
-            rolloff_bin[td.pitch_off + t + h] = first;
+        for (int c = 0; c < 12; ++c) {
+            mx.x = fmaxf(mx.x, fabsf(acc[c].x));
+            mx.y = fmaxf(mx.y, fabsf(acc[c].y));
         }
+        const float l0 = (mx.x < 1.1754943508222875e-38f) ? 1.0f : mx.x, l1 = (mx.y < 1.1754943508222875e-38f) ? 1.0f : mx.y;
+        float* dst = out + size_t(td.pitch_off) * 12 + t;
+#pragma unroll
+        for (int c = 0; c < 12; ++c) *reinterpret_cast<float2*>(dst + size_t(c) * td.ld) = make_float2(acc[c].x / l0, acc[c].y / l1);
+    }
+}
+
+#ifndef TA_TP_KT
+#define TA_TP_KT 8
+#endif
+#ifndef TA_TP_STAGES
+#define TA_TP_STAGES 3
+#endif
+static constexpr int TP_KT = TA_TP_KT;  // magnitude rows per pipeline stage
+static constexpr int TP_BOX = 256;      // frames per TMA box (the hardware limit per box dimension); a stage is two boxes
+static constexpr int TP_STAGES = TA_TP_STAGES;
+static constexpr int TP_STAGE_FLOATS = 2 * TP_KT * TP_BOX;
+
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    for (int spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1 << 24)) __trap();   // a transfer that never lands must abort the kernel, not hang the device
+    }
+}
+
+// The same walk as chroma_project_kernel (kept below as the reference formulation and for configurations whose filterbank
+// does not fit next to the pipeline), fed by the TMA unit: thread 0 issues, per stage, two cp.async.bulk.tensor loads of
+// {256 frames, 8 bins} boxes of the track's (bins, T) matrix into shared memory and the CTA consumes them behind an mbarrier
+// -- TP_STAGES * 16 KB in flight per CTA without a register or a scoreboard slot held, instead of eight 64-bit LDGs per
+// thread (75 % long-scoreboard stalls at 57 % of the HBM peak).  Frames past the end of the track and bins past the last one
+// arrive as zeros (the tensor map's extents are T and B).
+template <bool CHROMA, bool ROLL>
+__global__ void __launch_bounds__(CP_THREADS, 2) chroma_project_tma_kernel(const TrackDesc* __restrict__ tracks,
+                                                                           const CUtensorMap* __restrict__ maps,
+                                                                           const float* __restrict__ mag, const float* __restrict__ fb,
+                                                                           float* __restrict__ out, int32_t* __restrict__ rolloff_bin,
+                                                                           const float* __restrict__ frame_sum, float roll_percent,
+                                                                           int n_bins) {
+    using namespace p2;
+    extern __shared__ __align__(128) float tsm[];   // [TP_STAGES][2][TP_KT][TP_BOX] tiles | filterbank | barriers
+    float* wsm = tsm + TP_STAGES * TP_STAGE_FLOATS;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(wsm + (CHROMA ? ((n_bins * 12 + 1) & ~1) : 0));
+    const TrackDesc td = tracks[blockIdx.y];
+    const int f0 = blockIdx.x * CP_THREADS * 2;      // first frame of this CTA
+    if (f0 >= td.n_frames) return;
+    const int tid = threadIdx.x;
+    const int t = f0 + 2 * tid;
+    const bool ok = t < td.n_frames;
+    const unsigned tile0 = static_cast<unsigned>(__cvta_generic_to_shared(tsm));
+    const unsigned bar0 = static_cast<unsigned>(__cvta_generic_to_shared(bars));
+    const unsigned long long map = reinterpret_cast<unsigned long long>(maps + blockIdx.y);
+    const int n_groups = (n_bins + TP_KT - 1) / TP_KT;
+    auto issue = [&](int grp) {   // thread 0: both boxes of row group `grp` into stage grp % TP_STAGES
+        const int st = grp % TP_STAGES;
+        const unsigned bar = bar0 + 8 * st, dst = tile0 + st * TP_STAGE_FLOATS * 4;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(TP_STAGE_FLOATS * 4) : "memory");
+#pragma unroll
+        for (int bx = 0; bx < 2; ++bx)
+            asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                         ::"r"(dst + bx * TP_KT * TP_BOX * 4), "l"(map), "r"(f0 + bx * TP_BOX), "r"(grp * TP_KT), "r"(bar)
+                         : "memory");
+    };
+    if (tid == 0) {
+        for (int s = 0; s < TP_STAGES; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int gq = 0; gq < TP_STAGES && gq < n_groups; ++gq) issue(gq);
+    }
+    const float* __restrict__ w = fb + size_t(blockIdx.y) * n_bins * 12;
+    if (CHROMA)
+        for (int i = tid; i < n_bins * 12; i += CP_THREADS) wsm[i] = w[i];
+    __syncthreads();   // barriers initialised and the filterbank staged
+    float2 acc[12];
+#pragma unroll
+    for (int c = 0; c < 12; ++c) acc[c] = make_float2(0.f, 0.f);
+    RollState rs;
+    if (ROLL) roll_init(rs, frame_sum, size_t(td.pitch_off) + t, ok, ok && t + 1 < td.n_frames, roll_percent);
+    const int col = (2 * tid) % TP_BOX + ((2 * tid) / TP_BOX) * TP_KT * TP_BOX;   // this thread's frame pair inside a stage
+    for (int grp = 0; grp < n_groups; ++grp) {
+        const int st = grp % TP_STAGES;
+        mbar_wait(bar0 + 8 * st, (grp / TP_STAGES) & 1);
+        const float* tile = tsm + st * TP_STAGE_FLOATS + col;
+        const int kk = grp * TP_KT;
+        float2 m[TP_KT];
+#pragma unroll
+        for (int u = 0; u < TP_KT; ++u) m[u] = *reinterpret_cast<const float2*>(tile + u * TP_BOX);
+#pragma unroll
+        for (int u = 0; u < TP_KT; ++u) {
+            if (kk + u >= n_bins) break;   // rows past the last bin are zero-filled; they have no filterbank row
+            if (ROLL) roll_step(rs, m[u], kk + u);
+            if (CHROMA) {
+                const float* wk = wsm + (kk + u) * 12;
+                const float2 s2 = pmul(m[u], m[u]);
+                const float4 w0 = *reinterpret_cast<const float4*>(wk);
+                const float4 w1 = *reinterpret_cast<const float4*>(wk + 4);
+                const float4 w2 = *reinterpret_cast<const float4*>(wk + 8);
+                const float ww[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+#pragma unroll
+                for (int c = 0; c < 12; ++c) acc[c] = pfmas(s2, ww[c], acc[c]);
+            }
+        }
+        __syncthreads();   // every thread has read this stage: it may be refilled
+        if (tid == 0 && grp + TP_STAGES < n_groups) issue(grp + TP_STAGES);
+    }
+    if (!ok) return;
+    const float* __restrict__ colg = mag + size_t(td.pitch_off) * n_bins + t;
+    if (ROLL) {
+        rolloff_bin[td.pitch_off + t] = roll_finish(colg, td.ld, n_bins, roll_percent, rs.run.x, rs.lo.x, rs.kx, rs.before.x);
+        if (t + 1 < td.n_frames)
+            rolloff_bin[td.pitch_off + t + 1] = roll_finish(colg + 1, td.ld, n_bins, roll_percent, rs.run.y, rs.lo.y, rs.ky, rs.before.y);
     }
     if (CHROMA) {
         float2 mx = make_float2(0.f, 0.f);
@@ -389,15 +542,53 @@ int run_tuning(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_trac
     return TA_OK;
 }
 
+// One 2-d tensor map per track over its (bins, T) float32 magnitude matrix (row pitch ld), box = {256 frames, 8 bins}: what one
+// TMA load of the projection's pipeline fetches.  Extents are T and B, so partial tiles arrive zero-filled.
+static int build_magnitude_maps(const ta_plan* plan, const HostBatch& hb, const float* mag, void* d_maps, cudaStream_t stream) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return TA_ERR_UNSUPPORTED;
+    std::vector<CUtensorMap> maps(hb.n_tracks);
+    const int B = plan->n_bins;
+    for (int i = 0; i < hb.n_tracks; ++i) {
+        const TrackDesc& t = hb.tracks[i];
+        const cuuint64_t dims[2] = {cuuint64_t(t.n_frames), cuuint64_t(B)};
+        const cuuint64_t strides[1] = {cuuint64_t(t.ld) * sizeof(float)};
+        const cuuint32_t box[2] = {TP_BOX, TP_KT};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(mag) + size_t(t.pitch_off) * B, dims,
+                               strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return TA_ERR_UNSUPPORTED;
+    }
+    TA_CUDA(cudaMemcpyAsync(d_maps, maps.data(), sizeof(CUtensorMap) * hb.n_tracks, cudaMemcpyHostToDevice, stream));
+    return TA_OK;
+}
+
 template <bool CHROMA, bool ROLL>
 static int launch_project(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_tracks, const float* mag, const float* fb,
-                          float* chroma, int32_t* rolloff_bin, cudaStream_t stream) {
-    const size_t n_ck = (size_t(plan->n_bins) + ROLL_BLOCK - 1) / ROLL_BLOCK;
-    const size_t smem = (CHROMA ? size_t(plan->n_bins) * 12 * sizeof(float) : 0) + (ROLL ? n_ck * CP_THREADS * sizeof(float2) : 0);
+                          float* chroma, int32_t* rolloff_bin, const float* frame_sum, void* d_maps, cudaStream_t stream) {
+    if (ROLL && !frame_sum) {
+        set_error("the roll-off walk needs the per-frame magnitude sums of the STFT stage");
+        return TA_ERR_INVALID;
+    }
+    static const bool use_tma = [] { const char* e = std::getenv("TA_PROJECT"); return !(e && e[0] == 'l'); }();  // TA_PROJECT=ldg
+    const size_t tma_smem = size_t(TP_STAGES) * TP_STAGE_FLOATS * 4 + (CHROMA ? size_t(plan->n_bins) * 12 * sizeof(float) : 0) +
+                            TP_STAGES * 8 + 128;
+    if (use_tma && d_maps && tma_smem <= 113 * 1024 && build_magnitude_maps(plan, hb, mag, d_maps, stream) == TA_OK) {
+        auto kern = chroma_project_tma_kernel<CHROMA, ROLL>;
+        TA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem));
+        kern<<<dim3((hb.max_frames + 2 * CP_THREADS - 1) / (2 * CP_THREADS), hb.n_tracks), CP_THREADS, tma_smem, stream>>>(
+            d_tracks, reinterpret_cast<const CUtensorMap*>(d_maps), mag, fb, chroma, rolloff_bin, frame_sum,
+            float(plan->desc.roll_percent), plan->n_bins);
+        count_launch();
+        TA_CUDA(cudaGetLastError());
+        return TA_OK;
+    }
+    const size_t smem = CHROMA ? size_t(plan->n_bins) * 12 * sizeof(float) : 0;
     auto kern = chroma_project_kernel<CHROMA, ROLL>;
     TA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dim3((hb.max_frames + 2 * CP_THREADS - 1) / (2 * CP_THREADS), hb.n_tracks), CP_THREADS, smem, stream>>>(
-        d_tracks, mag, fb, chroma, rolloff_bin, float(plan->desc.roll_percent), plan->n_bins);
+        d_tracks, mag, fb, chroma, rolloff_bin, frame_sum, float(plan->desc.roll_percent), plan->n_bins);
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TA_OK;
@@ -405,12 +596,13 @@ static int launch_project(const ta_plan* plan, const HostBatch& hb, const TrackD
 
 // chroma (may be NULL) and / or the roll-off bins (may be NULL) from an existing magnitude spectrogram
 int run_chroma(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_tracks, const float* mag, const float* frame_max,
-               float* chroma, double* tuning, int32_t* rolloff_bin, void* scratch, size_t scratch_bytes, cudaStream_t stream) {
+               float* chroma, double* tuning, int32_t* rolloff_bin, const float* frame_sum, void* scratch, size_t scratch_bytes,
+               void* d_maps, cudaStream_t stream) {
     TA_REQUIRE(hb.n_tracks <= 65535, "at most 65535 tracks per call");
     TA_REQUIRE(mag && (reinterpret_cast<uintptr_t>(mag) & 15) == 0, "the magnitude buffer must be present and 16-byte aligned");
     if (!chroma) {
         if (!rolloff_bin) return TA_OK;
-        return launch_project<false, true>(plan, hb, d_tracks, mag, nullptr, nullptr, rolloff_bin, stream);
+        return launch_project<false, true>(plan, hb, d_tracks, mag, nullptr, nullptr, rolloff_bin, frame_sum, d_maps, stream);
     }
     TA_REQUIRE(plan->desc.n_chroma == 12, "only n_chroma = 12 is implemented");
     TA_REQUIRE(frame_max && tuning, "chroma needs the frame_max and tuning buffers");
@@ -423,8 +615,8 @@ int run_chroma(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_trac
     count_launch();
     TA_CUDA(cudaGetLastError());
     TA_REQUIRE((reinterpret_cast<uintptr_t>(chroma) & 15) == 0, "the chroma buffer must be 16-byte aligned");
-    return rolloff_bin ? launch_project<true, true>(plan, hb, d_tracks, mag, fb, chroma, rolloff_bin, stream)
-                       : launch_project<true, false>(plan, hb, d_tracks, mag, fb, chroma, nullptr, stream);
+    return rolloff_bin ? launch_project<true, true>(plan, hb, d_tracks, mag, fb, chroma, rolloff_bin, frame_sum, d_maps, stream)
+                       : launch_project<true, false>(plan, hb, d_tracks, mag, fb, chroma, nullptr, nullptr, d_maps, stream);
 }
 
 }  // namespace ta

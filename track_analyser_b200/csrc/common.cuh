@@ -105,7 +105,8 @@ int build_host_batch(const ta_plan* plan, const ta_batch* b, HostBatch& hb);
 struct Workspace {
     TrackDesc* d_tracks;       // [n_tracks]
     uint32_t* d_mel_max;       // [n_tracks]
-    void* d_tmaps;             // [n_tracks] CUtensorMap (128 bytes each) of the magnitude matrices, K1's TMA stores
+    float* d_frame_sum;        // [P] sum_f |X| per frame from K1 (approximate total for the roll-off walk)
+    void* d_tmaps;             // [n_tracks] CUtensorMap (128 bytes each) of the magnitude matrices: the projection's TMA loads
     double* d_granules;        // granule sums of the time-domain pass (three areas)
     size_t gran_doubles;
     double* d_fft;             // autocorrelation scratch (complex double) [..]

@@ -62,12 +62,14 @@ __global__ void __launch_bounds__(256) onset_flux_kernel(const TrackDesc* __rest
             acc[3] += fmaxf(0.f, d3 - d2);
         }
         if (FLUX) {
+            // max(0, x1 - x0) in float64 of float32 inputs: the sign is decided by the float32 comparison (exact), so the
+            // half-wave rectification is a predicated DADD instead of a float64 max (DSETP + two selects per element)
+            const float vl = __shfl_up_sync(0xffffffffu, v.w, 1);
             const double x0 = double(v.x), x1 = double(v.y), x2 = double(v.z), x3 = double(v.w);
-            const double xl = double(__shfl_up_sync(0xffffffffu, v.w, 1));
-            accl[0] += fmax(0.0, x0 - xl);
-            accl[1] += fmax(0.0, x1 - x0);
-            accl[2] += fmax(0.0, x2 - x1);
-            accl[3] += fmax(0.0, x3 - x2);
+            if (v.x > vl) accl[0] += x0 - double(vl);
+            if (v.y > v.x) accl[1] += x1 - x0;
+            if (v.z > v.y) accl[2] += x2 - x1;
+            if (v.w > v.z) accl[3] += x3 - x2;
         }
     };
     const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -289,7 +289,7 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 size_t td_granule_doubles(const ta_plan* plan, const HostBatch& hb);
 size_t chroma_scratch_bytes(const ta_plan* plan, const HostBatch& hb);
 int run_chroma(const ta_plan*, const HostBatch&, const TrackDesc*, const float* mag, const float* frame_max, float* chroma,
-               double* tuning, int32_t* rolloff_bin, void* scratch, size_t scratch_bytes, cudaStream_t);
+               double* tuning, int32_t* rolloff_bin, const float* frame_sum, void* scratch, size_t scratch_bytes, void* d_maps, cudaStream_t);
 int run_tempogram(const ta_plan*, const HostBatch&, const TrackDesc*, const float* env, float* out, cudaStream_t);
 int run_mfcc(const ta_plan*, const HostBatch&, const TrackDesc*, const float* mel, const uint32_t* mel_max, double* mfcc,
              cudaStream_t);
@@ -314,6 +314,7 @@ size_t carve_workspace(const ta_plan* plan, const HostBatch& hb, void* base, Wor
     ws.d_tracks = reinterpret_cast<TrackDesc*>(take(sizeof(TrackDesc) * hb.n_tracks));
     ws.d_mel_max = reinterpret_cast<uint32_t*>(take(sizeof(uint32_t) * hb.n_tracks));
     ws.d_tmaps = take(size_t(128) * hb.n_tracks);
+    ws.d_frame_sum = reinterpret_cast<float*>(take(sizeof(float) * size_t(hb.total_pitch)));
     // granule sums: K-weighted, momentary hop, short-term hop
     ws.gran_doubles = td_granule_doubles(plan, hb);
     ws.d_granules = reinterpret_cast<double*>(take(sizeof(double) * ws.gran_doubles));
@@ -457,7 +458,7 @@ int ta_stft_features(const ta_plan* plan, const ta_batch* batch, const ta_fronte
     if ((rc = run_stft_features(plan, hb, ws, out, st)) != TA_OK) return rc;
     // the roll-off bins come from a sequential walk down the magnitude columns (chroma.cu)
     if (out->rolloff_bin)
-        return run_chroma(plan, hb, ws.d_tracks, out->magnitude, nullptr, nullptr, nullptr, out->rolloff_bin, nullptr, 0, st);
+        return run_chroma(plan, hb, ws.d_tracks, out->magnitude, nullptr, nullptr, nullptr, out->rolloff_bin, ws.d_frame_sum, nullptr, 0, ws.d_tmaps, st);
     return TA_OK;
 }
 
@@ -508,7 +509,7 @@ int ta_chroma_stft(const ta_plan* plan, const ta_batch* batch, const float* magn
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int rc = prepare(plan, batch, workspace, workspace_bytes, st, hb, ws);
     if (rc != TA_OK) return rc;
-    return run_chroma(plan, hb, ws.d_tracks, magnitude, frame_max, chroma, tuning, nullptr, ws.d_chroma, ws.chroma_bytes, st);
+    return run_chroma(plan, hb, ws.d_tracks, magnitude, frame_max, chroma, tuning, nullptr, nullptr, ws.d_chroma, ws.chroma_bytes, ws.d_tmaps, st);
 }
 
 int ta_tempogram(const ta_plan* plan, const ta_batch* batch, const float* onset_env, float* tempogram, void* workspace,
@@ -637,7 +638,7 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
         cudaEventRecord(ev_k1, st);
         cudaStreamWaitEvent(aux, ev_k1, 0);
         if (need_proj && (rc = run_chroma(plan, hb, ws.d_tracks, out->magnitude, out->frame_max, out->chroma, out->tuning,
-                                          out->rolloff_bin, ws.d_chroma, ws.chroma_bytes, aux)) != TA_OK) {
+                                          out->rolloff_bin, ws.d_frame_sum, ws.d_chroma, ws.chroma_bytes, ws.d_tmaps, aux)) != TA_OK) {
             join();
             return rc;
         }
@@ -674,7 +675,7 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
     mark(4);
     if (need_proj && !chroma_done &&
         (rc = run_chroma(plan, hb, ws.d_tracks, out->magnitude, out->frame_max, out->chroma, out->tuning, out->rolloff_bin,
-                         ws.d_chroma, ws.chroma_bytes, st)) != TA_OK) {
+                         ws.d_frame_sum, ws.d_chroma, ws.chroma_bytes, ws.d_tmaps, st)) != TA_OK) {
         join();
         return rc;
     }

@@ -1,55 +1,8 @@
 // Host-side dispatch of the fused STFT kernel (stft_kernel.cuh); the kernels are instantiated per n_fft in
 // stft_n1024.cu / stft_n2048.cu / stft_n4096.cu so that they compile in parallel.
-#include <mutex>
-
 #include "stft_params.cuh"
 
 namespace ta {
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* sym = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(sym);
-    });
-    return fn;
-}
-
-// One 2-d tensor map per track over its (bins, T) float32 magnitude matrix (row pitch ld): box = {4 frames, 256 bins},
-// the shape of one store from a sub-tile of K1's shared-memory tile; extents are T and B, so partial tiles are clipped.
-static int build_magnitude_maps(const ta_plan* plan, const HostBatch& hb, float* mag, void* d_maps, cudaStream_t stream) {
-    EncodeTiledFn enc = encode_tiled_fn();
-    if (!enc) {
-        set_error("cuTensorMapEncodeTiled is not available from this driver");
-        return TA_ERR_CUDA;
-    }
-    std::vector<CUtensorMap> maps(hb.n_tracks);
-    const int B = plan->n_bins;
-    for (int i = 0; i < hb.n_tracks; ++i) {
-        const TrackDesc& t = hb.tracks[i];
-        const cuuint64_t dims[2] = {cuuint64_t(t.n_frames), cuuint64_t(B)};
-        const cuuint64_t strides[1] = {cuuint64_t(t.ld) * sizeof(float)};
-        const cuuint32_t box[2] = {4, 256};
-        const cuuint32_t estr[2] = {1, 1};
-        const CUresult r = enc(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, mag + size_t(t.pitch_off) * B, dims, strides, box, estr,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
-            return TA_ERR_CUDA;
-        }
-    }
-    TA_CUDA(cudaMemcpyAsync(d_maps, maps.data(), sizeof(CUtensorMap) * hb.n_tracks, cudaMemcpyHostToDevice, stream));
-    return TA_OK;
-}
 
 int stft_tile_frames(int n_fft) { return n_fft == 4096 ? 8 : (n_fft == 2048 ? 16 : 32); }
 int stft_transform_length(int n_fft) { return n_fft < 1024 ? 1024 : n_fft; }
@@ -73,16 +26,12 @@ int run_stft_features(const ta_plan* plan, const HostBatch& hb, const Workspace&
     p.mel_woff = plan->d_mel_woff;
     p.mel_w = plan->d_mel_w;
     p.mag = out->magnitude;
-    p.tmaps = nullptr;
-    if (out->magnitude) {
-        int rc = build_magnitude_maps(plan, hb, out->magnitude, ws.d_tmaps, stream);
-        if (rc != TA_OK) return rc;
-        p.tmaps = reinterpret_cast<const CUtensorMap*>(ws.d_tmaps);
-    }
+
     p.mel = (plan->desc.n_mels > 0) ? out->mel : nullptr;
     p.centroid = out->centroid;
     p.rolloff_bin = out->rolloff_bin;
     p.frame_max = out->frame_max;
+    p.frame_sum = out->rolloff_bin ? ws.d_frame_sum : nullptr;
     p.ltas = out->ltas;
     p.band_energy = out->band_energy;
     p.mel_max = p.mel ? ws.d_mel_max : nullptr;

@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
         // fp32 chunk sums s1 = sum |X|, s2 = sum (k-kb)|X|; centroid = df * sum_c (s2_c + kb_c*s1_c) / sum_c s1_c
         // combined in double.  (librosa rounds |X|/sum to float32 before the float64 dot product; that changes
         // the result by ~2e-9 relative.)
-        if (p.centroid || p.frame_max) {
+        if (p.centroid || p.frame_max || p.frame_sum) {
             for (int fp = warp; 2 * fp < nf; fp += S::THREADS / 32) {   // warp per frame PAIR: one 64-bit read serves both
                 const float* col = tile + 2 * fp;
                 const int kb = lane * CH, ke = min(kb + CH, B);
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
                     if (f >= nf) break;  // warp-uniform
                     const float s1 = h ? q1.y : q1.x, s2 = h ? q2.y : q2.x;
                     float s3 = h ? q3.y : q3.x;
-                    if (p.centroid) {
+                    if (p.centroid || p.frame_sum) {
                         double den = double(s1), num = double(s2) + double(kb) * double(s1);
 #pragma unroll
                         for (int o = 16; o > 0; o >>= 1) {
@@ -413,7 +413,8 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
                         }
                         if (lane == 0) {
                             const double df = p.freqs[1];
-                            p.centroid[col_out(td, t0, f)] = (den < 1.1754943508222875e-38) ? df * num : df * num / den;
+                            if (p.centroid) p.centroid[col_out(td, t0, f)] = (den < 1.1754943508222875e-38) ? df * num : df * num / den;
+                            if (p.frame_sum) p.frame_sum[col_out(td, t0, f)] = float(den);
                         }
                     }
                     if (p.frame_max) {

@@ -1,7 +1,5 @@
 // Parameter block of the fused STFT kernel and the per-n_fft launchers (stft_n*.cu).
 #pragma once
-#include <cuda.h>
-
 #include "common.cuh"
 
 namespace ta {
@@ -24,12 +22,12 @@ struct StftParams {
     const int* mel_woff;
     const float* mel_w;
     // outputs (nullable)
-    const CUtensorMap* tmaps;  // [n_tracks] tensor maps of the per-track (bins, T) magnitude matrices, or nullptr: no magnitude
     float* mag;
     float* mel;
     double* centroid;
     int32_t* rolloff_bin;
     float* frame_max;     // [P] max_f |X|
+    float* frame_sum;     // [P] sum_f |X| (float32 chunk sums combined in double): the roll-off walk's first estimate of its total
     double* ltas;         // [n_tracks][B]
     double* band_energy;  // [n_tracks][2][B]
     uint32_t* mel_max;    // [n_tracks]
