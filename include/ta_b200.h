@@ -137,6 +137,8 @@ typedef struct ta_frontend_out {
     float* hpss_scratch;   /* [B * P]  caller-provided scratch (time-direction medians); required with the two above */
     double* mfcc;          /* [TA_N_MFCC * P] librosa.feature.mfcc(S=power_to_db(mel + 1e-9), n_mfcc=13), float64:
                               analysis/structure.py:192,199 (needs mel) */
+    double* self_similarity; /* [P]    MFCC self-similarity novelty (Gaussian-smoothed cepstrum, 2 s context windows, 1 - cosine):
+                              analysis/structure.py:199-210 (needs mfcc) */
     float* chroma_cqt;     /* [12 * Pc] librosa.feature.chroma_cqt(y, sr), inf-normalised per frame: harmony.py:107,148.
                               Pc = sum_i ta_frame_pitch(ta_cqt_frame_count(plan, n_samples[i])); needs magnitude, frame_max,
                               cqt_tuning and cqt_scratch; plan must be n_fft 2048 / hop 512 (librosa's defaults there) */

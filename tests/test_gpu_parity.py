@@ -854,3 +854,36 @@ def test_resample_errors_and_coerce_audio_paths(tmp_path):
 
     res = pipeline.analyse_track(str(path))
     assert res.audio.sample_rate == 44_100 and len(res.audio.samples) == len(want)
+
+
+def test_self_similarity_novelty_on_the_device():
+    """K13 (csrc/novelty.cu): the MFCC self-similarity curve of analysis/structure.py:199-210 against the host formula
+    (scipy gaussian_filter1d + numpy window means) applied to the device's own cepstrum, and end to end against the oracle."""
+    import scipy.ndimage
+
+    sr = 44_100
+    tracks = [synth.synth_track(21, 11.0, sr, 2), synth.synth_track(22, 5.5, sr, 2), synth.synth_track(23, 3.0, sr, 2)]
+    res = engine.analyse_batch(plan_for(sr), tracks, ("self_similarity", "mfcc"))
+
+    def host(mfcc, context):
+        frames = mfcc.shape[1]
+        sm = scipy.ndimage.gaussian_filter1d(mfcc, sigma=1.0, axis=1)
+        out = np.zeros(frames)
+        if frames > 2 * context:
+            means = np.lib.stride_tricks.sliding_window_view(sm, context, axis=1).mean(axis=2)
+            unit = means / (np.linalg.norm(means, axis=0) + 1e-9)
+            f = np.arange(context, frames - context)
+            out[f] = 1.0 - np.sum(unit[:, f - context] * unit[:, f], axis=0)
+        return out
+
+    context = int(round(2.0 * sr / 512))
+    for r, x in zip(res, tracks):
+        want = host(np.asarray(r["mfcc"]), context)
+        assert r["self_similarity"].shape == want.shape and r["self_similarity"].dtype == np.float64
+        # same orders of evaluation as scipy / numpy: float64 round-off only (1 - cosine of nearly parallel vectors cancels)
+        np.testing.assert_allclose(r["self_similarity"], want, rtol=0, atol=5e-15)
+        mono = np.mean(x, axis=0) if x.ndim == 2 else x
+        mel = olr.melspectrogram(mono, sr, n_fft=2048, hop_length=512, n_mels=128)
+        ref = host(olr.mfcc(olr.power_to_db(np.asarray(mel, dtype=float) + 1e-9)), context)
+        np.testing.assert_allclose(r["self_similarity"], ref, rtol=RTOL, atol=1e-7)
+    assert np.all(res[2]["self_similarity"] == 0.0)   # 3 s < two context windows: the reference leaves the curve at zero

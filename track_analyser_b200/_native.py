@@ -84,6 +84,7 @@ class FrontendOut(C.Structure):
         ("hpss_percussive", C.c_void_p),
         ("hpss_scratch", C.c_void_p),
         ("mfcc", C.c_void_p),
+        ("self_similarity", C.c_void_p),
         ("chroma_cqt", C.c_void_p),
         ("cqt_tuning", C.c_void_p),
         ("cqt_mag", C.c_void_p),

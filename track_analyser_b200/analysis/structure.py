@@ -49,6 +49,7 @@ class StructureFrontend:
     harmonic_curve: np.ndarray | None = None    # (T,) sum over bins of hpss(magnitude)[0]
     percussive_curve: np.ndarray | None = None  # (T,) sum over bins of hpss(magnitude)[1]
     mfcc: np.ndarray | None = None              # (13, T) float64 mfcc(S=log_mel) from csrc/mfcc.cu -- structure.py:199
+    self_similarity: np.ndarray | None = None   # (T,) float64 MFCC self-similarity from csrc/novelty.cu -- structure.py:199-210
 
 
 def power_to_db(S: np.ndarray, amin: float = 1e-10, top_db: float = 80.0) -> np.ndarray:
@@ -64,7 +65,8 @@ def structure_frontend(audio: AudioInput, *, frame_length: int = 2048, hop_lengt
     (128, T) mel matrix in HBM as well and brings back its 13-row cepstrum instead."""
     if not isinstance(audio, AudioInput):
         raise TypeError("analyse_structure expects an AudioInput instance")
-    outs = ("flux_linear", "hpss_harmonic", "hpss_percussive", "mfcc") + (("mel",) if matrices else ()) + \
+    # matrices=False: the self-similarity curve is formed on the device too, so not even the cepstrum travels
+    outs = ("flux_linear", "hpss_harmonic", "hpss_percussive") + (("mfcc", "mel") if matrices else ("self_similarity",)) + \
            (("magnitude",) if magnitude else ())
     res = runtime.frontend(np.asarray(audio.samples, dtype=np.float32), audio.sample_rate, n_fft=frame_length,
                            hop=hop_length, outputs=outs)
@@ -72,7 +74,7 @@ def structure_frontend(audio: AudioInput, *, frame_length: int = 2048, hop_lengt
         return StructureFrontend(magnitude=res["magnitude"] if (magnitude and "magnitude" in res) else None, mel=None,
                                  log_mel=None, spectral_flux=np.asarray(res["flux_linear"], dtype=float),
                                  harmonic_curve=np.asarray(res["hpss_harmonic"]), percussive_curve=np.asarray(res["hpss_percussive"]),
-                                 mfcc=np.asarray(res["mfcc"]))
+                                 self_similarity=np.asarray(res["self_similarity"], dtype=float))
     mel64 = np.asarray(res["mel"], dtype=float)
     # inside a session the fused run holds every output; the 64 MB magnitude is only copied back when asked for
     return StructureFrontend(magnitude=res["magnitude"] if (magnitude and "magnitude" in res) else None, mel=res["mel"],
@@ -91,10 +93,14 @@ def _unit_range(curve: np.ndarray) -> np.ndarray:
 
 def novelty_curves(log_mel: np.ndarray | None, spectral_flux: np.ndarray, percussive_curve: np.ndarray,
                    harmonic_curve: np.ndarray, *, hop_length: int, sample_rate: int, context_seconds: float = 2.0,
-                   mfcc: np.ndarray | None = None) -> Tuple[np.ndarray, np.ndarray]:
+                   mfcc: np.ndarray | None = None, self_similarity: np.ndarray | None = None) -> Tuple[np.ndarray, np.ndarray]:
     """(smoothed combined novelty, normalised energy novelty): structure.py:182-224 from the device curves.
 
-    ``mfcc``: the (13, T) cepstrum when it was already formed (on the device); else it is derived from log_mel."""
+    ``self_similarity``: the MFCC self-similarity curve when the device formed it (csrc/novelty.cu); else it is derived
+    here from ``mfcc`` (the (13, T) cepstrum, device or host), itself derived from ``log_mel`` when absent."""
+    if self_similarity is not None:
+        return _mix_novelty(np.asarray(self_similarity, dtype=float), spectral_flux, percussive_curve, harmonic_curve,
+                            hop_length=hop_length, sample_rate=sample_rate)
     if mfcc is None:
         # librosa.feature.mfcc(S=log_mel, n_mfcc=13): orthonormal DCT-II along the mel axis, first 13 rows
         mfcc = scipy.fft.dct(np.asarray(log_mel, dtype=float), axis=0, type=2, norm="ortho")[:13]
@@ -109,6 +115,14 @@ def novelty_curves(log_mel: np.ndarray | None, spectral_flux: np.ndarray, percus
         unit = means / (np.linalg.norm(means, axis=0) + 1e-9)
         f = np.arange(context, frames - context)
         self_similarity[f] = 1.0 - np.sum(unit[:, f - context] * unit[:, f], axis=0)
+    return _mix_novelty(self_similarity, spectral_flux, percussive_curve, harmonic_curve, hop_length=hop_length,
+                        sample_rate=sample_rate)
+
+
+def _mix_novelty(self_similarity: np.ndarray, spectral_flux: np.ndarray, percussive_curve: np.ndarray,
+                 harmonic_curve: np.ndarray, *, hop_length: int, sample_rate: int) -> Tuple[np.ndarray, np.ndarray]:
+    """structure.py:211-224: percussive-ratio energy novelty and the 0.5 / 0.3 / 0.2 mix, smoothed."""
+    frames = self_similarity.shape[0]
     perc = np.asarray(percussive_curve) if np.size(percussive_curve) else np.zeros(frames)
     harm = np.asarray(harmonic_curve) if np.size(harmonic_curve) else np.zeros(frames)
     ratio = perc / (perc + harm + 1e-9)
@@ -202,12 +216,14 @@ def boundaries_from_curves(novelty: np.ndarray, energy_novelty: np.ndarray, beat
 
 def segments_from_curves(frontend: StructureFrontend, beat_result: BeatAnalysis, *, sample_rate: int, hop_length: int,
                          duration: float) -> StructureAnalysis:
-    if (frontend.mel if frontend.mel is not None else frontend.mfcc).size == 0:
+    probe = next(a for a in (frontend.mel, frontend.mfcc, frontend.self_similarity) if a is not None)
+    if probe.size == 0:
         raise ValueError("not enough values to unpack (expected 2, got 0)")  # the reference's behaviour on empty audio
     # the cepstrum computed next to the mel matrix on the device is used when the matrix itself stayed there
     novelty, energy_novelty = novelty_curves(frontend.log_mel, frontend.spectral_flux, frontend.percussive_curve,
                                              frontend.harmonic_curve, hop_length=hop_length, sample_rate=sample_rate,
-                                             mfcc=frontend.mfcc if frontend.log_mel is None else None)
+                                             mfcc=frontend.mfcc if frontend.log_mel is None else None,
+                                             self_similarity=frontend.self_similarity)
     frames, times = boundaries_from_curves(novelty, energy_novelty, beat_result.beat_times, sample_rate=sample_rate,
                                            hop_length=hop_length)
     labels = [chr(ord("A") + i % 26) for i in range(len(frames) - 1)]

@@ -105,6 +105,7 @@ int build_host_batch(const ta_plan* plan, const ta_batch* b, HostBatch& hb);
 struct Workspace {
     TrackDesc* d_tracks;       // [n_tracks]
     uint32_t* d_mel_max;       // [n_tracks]
+    double* d_novelty;         // [2 * TA_N_MFCC * P] smoothed cepstrum and unit window means (self-similarity, K13)
     float* d_frame_sum;        // [P] sum_f |X| per frame from K1 (approximate total for the roll-off walk)
     void* d_tmaps;             // [n_tracks] CUtensorMap (128 bytes each) of the magnitude matrices: the projection's TMA loads
     double* d_granules;        // granule sums of the time-domain pass (three areas)

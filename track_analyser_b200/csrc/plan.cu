@@ -295,6 +295,8 @@ int run_mfcc(const ta_plan*, const HostBatch&, const TrackDesc*, const float* me
              cudaStream_t);
 int run_hpss(const ta_plan*, const HostBatch&, const TrackDesc*, const float* mag, float* scratch, float* harm_sum, float* perc_sum,
              cudaStream_t);
+int run_self_similarity(const ta_plan*, const HostBatch&, const TrackDesc*, const double* mfcc, double* scratch, double* out,
+                        cudaStream_t);
 
 int cqt_supported(const ta_plan* plan);
 int64_t cqt_frame_count(const ta_plan* plan, int64_t n_samples);
@@ -315,6 +317,7 @@ size_t carve_workspace(const ta_plan* plan, const HostBatch& hb, void* base, Wor
     ws.d_mel_max = reinterpret_cast<uint32_t*>(take(sizeof(uint32_t) * hb.n_tracks));
     ws.d_tmaps = take(size_t(128) * hb.n_tracks);
     ws.d_frame_sum = reinterpret_cast<float*>(take(sizeof(float) * size_t(hb.total_pitch)));
+    ws.d_novelty = reinterpret_cast<double*>(take(plan->desc.n_mels > 0 ? sizeof(double) * 2 * TA_N_MFCC * size_t(hb.total_pitch) : 0));
     // granule sums: K-weighted, momentary hop, short-term hop
     ws.gran_doubles = td_granule_doubles(plan, hb);
     ws.d_granules = reinterpret_cast<double*>(take(sizeof(double) * ws.gran_doubles));
@@ -664,6 +667,13 @@ static int frontend_impl(const ta_plan* plan, const ta_batch* batch, const ta_fr
         if (!out->mel) { join(); set_error("mfcc output needs the mel output buffer"); return TA_ERR_INVALID; }
         if ((rc = run_mfcc(plan, hb, ws.d_tracks, out->mel, ws.d_mel_max, out->mfcc, st)) != TA_OK) { join(); return rc; }
     }
+    if (out->self_similarity) {
+        if (!out->mfcc) { join(); set_error("self_similarity output needs the mfcc output buffer"); return TA_ERR_INVALID; }
+        if ((rc = run_self_similarity(plan, hb, ws.d_tracks, out->mfcc, ws.d_novelty, out->self_similarity, st)) != TA_OK) {
+            join();
+            return rc;
+        }
+    }
     mark(2);
     if (out->autocorr &&
         (rc = run_autocorrelate(plan, hb, ws.d_tracks, out->onset_env, out->autocorr, ws.d_fft, ws.fft_elems, st)) != TA_OK) {
@@ -752,7 +762,7 @@ int ta_frontend_run_host(const ta_plan* plan, const ta_batch* hbatch, const ta_f
     }
     // dependency closure: buffers the schedule needs on the device although the caller did not ask for them
     const bool w_tempo = hout->tempogram, w_ac = hout->autocorr, w_env = hout->onset_env || w_ac || w_tempo;
-    const bool w_mel = hout->mel || w_env || hout->flux_linear || hout->mfcc;
+    const bool w_mel = hout->mel || w_env || hout->flux_linear || hout->mfcc || hout->self_similarity;
     const bool w_chroma = hout->chroma || hout->tuning;
     const bool w_hpss = hout->hpss_harmonic || hout->hpss_percussive;
     const bool w_mag = hout->magnitude || w_chroma || w_hpss || want_cqt || hout->rolloff_bin;
@@ -793,7 +803,8 @@ int ta_frontend_run_host(const ta_plan* plan, const ta_batch* hbatch, const ta_f
     d.hpss_harmonic = (float*)want(w_hpss, hout->hpss_harmonic, P * 4);
     d.hpss_percussive = (float*)want(w_hpss, hout->hpss_percussive, P * 4);
     d.hpss_scratch = (float*)want(w_hpss, nullptr, B * P * 4);
-    d.mfcc = (double*)want(false, hout->mfcc, size_t(TA_N_MFCC) * P * 8);
+    d.mfcc = (double*)want(hout->self_similarity != nullptr, hout->mfcc, size_t(TA_N_MFCC) * P * 8);
+    d.self_similarity = (double*)want(false, hout->self_similarity, P * 8);
     d.chroma_cqt = (float*)want(want_cqt, hout->chroma_cqt, 12 * Pc * 4);
     d.cqt_tuning = (double*)want(want_cqt, hout->cqt_tuning, nt * 8);
     d.cqt_mag = (float*)want(false, hout->cqt_mag, 252 * Pc * 4);

@@ -27,15 +27,15 @@ _TRACE_FETCH = os.environ.get("TA_TRACE_FETCH", "0") not in ("", "0")  # debuggi
 ALL_OUTPUTS = (
     "magnitude", "mel", "onset_env", "autocorr", "flux_linear", "ltas", "centroid", "rolloff_bin",
     "band_energy", "moments", "kw_blocks", "lufs", "rms_momentary", "rms_short", "frame_max", "chroma", "tuning",
-    "tempogram", "true_peak", "hpss_harmonic", "hpss_percussive", "mfcc", "chroma_cqt", "cqt_tuning", "cqt_mag",
+    "tempogram", "true_peak", "hpss_harmonic", "hpss_percussive", "mfcc", "self_similarity", "chroma_cqt", "cqt_tuning", "cqt_mag",
 )
 # SURVEY section 8a (the north-star frontend): what bench.py measures.  true_peak, the HPSS curves and the MFCC are
 # section-8f "next" rows.
-_NEXT_ROWS = ("true_peak", "hpss_harmonic", "hpss_percussive", "mfcc", "chroma_cqt", "cqt_tuning", "cqt_mag")
+_NEXT_ROWS = ("true_peak", "hpss_harmonic", "hpss_percussive", "mfcc", "self_similarity", "chroma_cqt", "cqt_tuning", "cqt_mag")
 FRONTEND_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o not in _NEXT_ROWS)
 # What the host-side stages of pipeline.analyse_track consume: neither the magnitude (HPSS runs on the device), nor the
 # mel matrix (its only host consumer, the MFCC, runs on the device) nor the plot-only tempogram leave the GPU.
-ANALYSIS_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o not in ("magnitude", "mel", "tempogram", "cqt_mag"))
+ANALYSIS_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o not in ("magnitude", "mel", "tempogram", "cqt_mag", "mfcc"))
 # the bench / default frontend: everything the per-track analysis consumes except the plot-only tempogram (and the
 # constant-Q chroma, which only the 2048/512 plan of the harmony stage can produce: ask for it explicitly)
 CORE_OUTPUTS = tuple(o for o in ALL_OUTPUTS if o not in ("tempogram", "chroma_cqt", "cqt_tuning", "cqt_mag"))
@@ -53,7 +53,7 @@ def available_outputs(plan: "Plan", outputs: Iterable[str] = ALL_OUTPUTS) -> tup
     ones unless it is librosa's chroma_cqt configuration (n_fft 2048, hop 512, basis below the Nyquist frequency)."""
     drop = set()
     if plan.n_mels == 0:
-        drop |= {"mel", "onset_env", "autocorr", "flux_linear", "tempogram", "mfcc"}
+        drop |= {"mel", "onset_env", "autocorr", "flux_linear", "tempogram", "mfcc", "self_similarity"}
     if not plan.cqt_ok:
         drop |= {"chroma_cqt", "cqt_tuning", "cqt_mag"}
     return tuple(o for o in outputs if o not in drop)
@@ -340,6 +340,8 @@ class FrontendBuffers:
         if unknown:
             raise ValueError(f"unknown outputs {sorted(unknown)}")
         self.requested = tuple(o for o in ALL_OUTPUTS if o in outputs)  # what the caller asked for (the rest are intermediates)
+        if "self_similarity" in outputs:
+            outputs.add("mfcc")
         if outputs & {"onset_env", "autocorr", "flux_linear", "mfcc"}:
             outputs.add("mel")
         if outputs & {"autocorr", "tempogram"}:
@@ -371,7 +373,7 @@ class FrontendBuffers:
             "frame_max": ((P,), torch.float32), "chroma": ((12 * P,), torch.float32), "tuning": ((nt,), torch.float64),
             "tempogram": ((plan.tempogram_win * P,), torch.float32), "true_peak": ((nt,), torch.float32),
             "hpss_harmonic": ((P,), torch.float32), "hpss_percussive": ((P,), torch.float32),
-            "mfcc": ((N_MFCC * P,), torch.float64),
+            "mfcc": ((N_MFCC * P,), torch.float64), "self_similarity": ((P,), torch.float64),
             "chroma_cqt": ((12 * Pc,), torch.float32), "cqt_tuning": ((nt,), torch.float64),
             "cqt_mag": ((N_CQT_BINS * Pc,), torch.float32),
         }
@@ -455,7 +457,7 @@ def _cut(plan: Plan, batch: DeviceBatch, i: int, k: str, h: np.ndarray):
     if k in ("tuning", "lufs", "true_peak", "cqt_tuning"):
         return float(h[i])
     if k in ("onset_env", "autocorr", "flux_linear", "centroid", "rolloff_bin", "frame_max", "hpss_harmonic",
-             "hpss_percussive"):
+             "hpss_percussive", "self_similarity"):
         return h[po: po + T]
     if k == "kw_blocks":
         return h[i, : plan.kw_block_count(ns)]
@@ -544,7 +546,7 @@ def _output_specs(plan: Plan, batch: DeviceBatch, kw_pitch: int, rms_pitch: int,
         "moments": (nt * N_MOMENTS, f64), "kw_blocks": (nt * kw_pitch, f64), "lufs": (nt, f64),
         "rms_momentary": (nt * rms_pitch, f64), "rms_short": (nt * rms_pitch, f64), "frame_max": (P, f32),
         "chroma": (12 * P, f32), "tuning": (nt, f64), "tempogram": (plan.tempogram_win * P, f32), "true_peak": (nt, f32),
-        "hpss_harmonic": (P, f32), "hpss_percussive": (P, f32), "mfcc": (N_MFCC * P, f64),
+        "hpss_harmonic": (P, f32), "hpss_percussive": (P, f32), "mfcc": (N_MFCC * P, f64), "self_similarity": (P, f64),
         "chroma_cqt": (12 * Pc, f32), "cqt_tuning": (nt, f64), "cqt_mag": (N_CQT_BINS * Pc, f32),
     }
 

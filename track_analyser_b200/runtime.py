@@ -148,7 +148,7 @@ def _plan_outputs(plan: engine.Plan, n_mels: int, n_samples: int, outs) -> tuple
     if n_samples < plan.meter_block * plan.sample_rate:
         outs = tuple(o for o in outs if o not in ("kw_blocks", "lufs"))
     if n_mels == 0:
-        outs = tuple(o for o in outs if o not in ("mel", "onset_env", "autocorr", "flux_linear", "tempogram", "mfcc"))
+        outs = tuple(o for o in outs if o not in ("mel", "onset_env", "autocorr", "flux_linear", "tempogram", "mfcc", "self_similarity"))
     if not plan.cqt_ok:
         outs = tuple(o for o in outs if o not in _CQT_OUTPUTS)
     return outs
