@@ -225,11 +225,12 @@ TA_API int ta_chroma_stft(const ta_plan* plan, const ta_batch* batch, const floa
 TA_API int ta_decode_pcm(const void* interleaved, int format, int channels, int64_t n_frames, float* planar_out,
                          void* stream);
 
-/* Is `mono` (n_samples floats) exactly the float32 mean of the planar pair `planar_stereo` (L then R, n_samples each), the
- * way utils.coerce_audio builds AudioInput.samples from stereo_samples (utils.py:116)?  ORs 1 into *mismatch (device int32,
- * zeroed by the caller) if any sample differs.  The batch driver uses it to decide whether one stereo run may serve the
- * mono stages of a track too (mono == mid exactly); NaNs count as a mismatch. */
-TA_API int ta_mono_mix_check(const float* planar_stereo, const float* mono, int64_t n_samples, int32_t* mismatch, void* stream);
+/* Fingerprint of the float32 mono mix (L[i] + R[i]) * 0.5f of the planar pair `planar_stereo` (L then R, n_samples each):
+ * fingerprint[0] = sum of the IEEE bit patterns, fingerprint[1] = sum of bit pattern * ((i & 0xffff) + 1), modulo 2^64
+ * (device uint64[2], written by the call).  The batch driver forms the same sums over AudioInput.samples on the host: equal
+ * fingerprints mean the mono samples are the mean of the stereo pair, the way utils.coerce_audio builds them (utils.py:116),
+ * and one stereo run may then serve the mono stages of the track too (mono == mid exactly). */
+TA_API int ta_mono_mix_fingerprint(const float* planar_stereo, int64_t n_samples, uint64_t* fingerprint, void* stream);
 
 /* K9: per-frame sums of the harmonic and percussive components of librosa.decompose.hpss (31-wide median
  * filters along time and frequency, soft masks with power 2) on an existing magnitude spectrogram:

@@ -15,6 +15,11 @@ n_tracks = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 workers = int(sys.argv[2]) if len(sys.argv) > 2 else None
 sr = 44_100
 base = [synth.synth_track(1 + i, 180.0, sr, 2) for i in range(4)]
+if os.environ.get("TA_PINNED"):   # like bench.py: the stereo pairs live in pinned host memory
+    import torch
+
+    pinned = [torch.from_numpy(x).pin_memory() for x in base]
+    base = [t.numpy() for t in pinned]
 audios = [AudioInput(samples=np.mean(x, axis=0), sample_rate=sr, stereo_samples=x) for x in base]
 srcs = [audios[i % 4] for i in range(n_tracks)]
 pipeline.analyse_tracks(srcs[:8], workers=workers)

@@ -119,7 +119,7 @@ SYMBOLS = {
     "ta_cqt_scratch_bytes": (C.c_size_t, [C.c_void_p, C.POINTER(Batch)]),
     "ta_chroma_cqt": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
-    "ta_mono_mix_check": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
+    "ta_mono_mix_fingerprint": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "ta_decode_pcm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p]),
     "ta_hpss_curves": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "ta_tempogram": (C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

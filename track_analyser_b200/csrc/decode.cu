@@ -27,26 +27,41 @@ __global__ void __launch_bounds__(256) decode_pcm_kernel(const unsigned char* __
         for (int c = 0; c < channels; ++c) dst[(size_t)c * n_frames + f] = pcm_sample<FMT>(src, size_t(f) * channels + c);
 }
 
-// mismatch |= any((L[i] + R[i]) * 0.5f != mono[i]): is `mono` exactly the float32 mean of the planar pair (utils.py:116)?
-__global__ void __launch_bounds__(256) mono_mix_check_kernel(const float* __restrict__ left, const float* __restrict__ right,
-                                                            const float* __restrict__ mono, long long n, int* __restrict__ mismatch) {
+// Fingerprint of the float32 mono mix (L[i] + R[i]) * 0.5f of a planar pair: fp[0] = sum of the bit patterns, fp[1] = sum of
+// bit pattern * ((i & 0xffff) + 1), both modulo 2^64.  The host forms the same two sums over AudioInput.samples; equal
+// fingerprints mean the mono samples are the mean of the stereo pair (utils.py:116) without uploading them.
+__global__ void __launch_bounds__(256) mono_mix_fingerprint_kernel(const float* __restrict__ left, const float* __restrict__ right,
+                                                                  long long n, unsigned long long* __restrict__ fp) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    bool bad = false;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
-        bad |= !(__fmul_rn(__fadd_rn(left[i], right[i]), 0.5f) == mono[i]);
-    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(mismatch, 1);
+    unsigned long long s1 = 0, s2 = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const unsigned long long b = __float_as_uint(__fmul_rn(__fadd_rn(left[i], right[i]), 0.5f));
+        s1 += b;
+        s2 += b * (unsigned long long)((i & 0xffff) + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(fp, s1);
+        atomicAdd(fp + 1, s2);
+    }
 }
 
 }  // namespace ta
 
-extern "C" int ta_mono_mix_check(const float* planar_stereo, const float* mono, int64_t n_samples, int32_t* mismatch, void* stream) {
+extern "C" int ta_mono_mix_fingerprint(const float* planar_stereo, int64_t n_samples, uint64_t* fingerprint, void* stream) {
     using namespace ta;
-    TA_REQUIRE(planar_stereo && mono && mismatch, "pointers must not be NULL");
+    TA_REQUIRE(planar_stereo && fingerprint, "pointers must not be NULL");
     TA_REQUIRE(n_samples >= 0, "n_samples must be >= 0");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    TA_CUDA(cudaMemsetAsync(fingerprint, 0, 2 * sizeof(uint64_t), st));
     if (n_samples == 0) return TA_OK;
     const int grid = int(std::min<long long>((n_samples + 255) / 256, 148 * 8));
-    mono_mix_check_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(planar_stereo, planar_stereo + n_samples, mono,
-                                                                                   n_samples, mismatch);
+    mono_mix_fingerprint_kernel<<<grid, 256, 0, st>>>(planar_stereo, planar_stereo + n_samples, n_samples,
+                                                      reinterpret_cast<unsigned long long*>(fingerprint));
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TA_OK;

@@ -265,6 +265,7 @@ def pack_host(tracks: Sequence[np.ndarray], channels: int, pinned: bool = True, 
 
 
 _pack_pool = None
+_COPY_PIECE = 2 << 20   # floats per host-to-device copy (8 MB)
 
 
 def upload(plan: Plan, tracks: Sequence[np.ndarray]) -> DeviceBatch:
@@ -306,7 +307,11 @@ def upload(plan: Plan, tracks: Sequence[np.ndarray]) -> DeviceBatch:
             if n == 0:
                 continue
             src = f if pinned[i] else torch.from_numpy(host[off: off + n])
-            dev[off: off + n].copy_(src, non_blocking=True)
+            # pieces of 8 MB: the small descriptor uploads of a frontend run on another stream queue behind whatever the
+            # copy engine is busy with, and must not wait for a whole 64 MB track
+            for a in range(0, n, _COPY_PIECE):
+                b = min(n, a + _COPY_PIECE)
+                dev[off + a: off + b].copy_(src[a:b], non_blocking=True)
         torch.cuda.current_stream(dev.device).synchronize()
     return DeviceBatch(plan, dev, offsets, n_samples, channels)
 

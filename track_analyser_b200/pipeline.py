@@ -203,6 +203,22 @@ def _stage_worker(task):
     return stages
 
 
+def _mono_fingerprint(mono) -> tuple:
+    """(sum of the float32 bit patterns, sum of bit pattern * ((i & 0xffff) + 1)) modulo 2^64: what
+    ``ta_mono_mix_fingerprint`` forms on the device from the stereo pair."""
+    b = np.ascontiguousarray(mono, dtype=np.float32).view(np.uint32)
+    n = b.shape[0]
+    m = n // 65536
+    col = np.zeros(65536, dtype=np.uint64)
+    if m:
+        col += b[: m * 65536].reshape(m, 65536).sum(axis=0, dtype=np.uint64)
+    col[: n - m * 65536] += b[m * 65536:]
+    with np.errstate(over="ignore"):
+        s1 = int(col.sum(dtype=np.uint64))
+        s2 = int((col * np.arange(1, 65537, dtype=np.uint64)).sum(dtype=np.uint64))
+    return s1, s2
+
+
 def _batch_buffer(audio: AudioInput):
     """(buffer for the batched run, channels) from the shapes and dtypes alone: the planar float32 stereo pair, or the mono
     samples of a track without one; None for layouts the batched path does not take."""
@@ -314,7 +330,7 @@ def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] 
     def uploader():
         try:
             stream = torch.cuda.Stream(dev_index)
-            with torch.cuda.stream(stream):
+            with cf.ThreadPoolExecutor(max_workers=8) as tp, torch.cuda.stream(stream):
                 for sr, ch, idxs in chunks:
                     cand, bad = [], []
                     for i in idxs:
@@ -323,21 +339,22 @@ def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] 
                     batch, good = None, []
                     if cand:
                         plan_a = runtime.get_plan(sr, *_PLAN_A, device=device)
+                        # (the host half of the fingerprints runs in the pool while the PCM travels)
+                        host_fp = [tp.submit(_mono_fingerprint, audios[i].samples) for i, _ in cand] if ch == 2 else []
                         batch = engine.upload(plan_a, [c[0] for _, c in cand])
                         ok = [True] * len(cand)
                         if ch == 2:
                             # one stereo run may serve the mono stages only if mono == mean(stereo) sample for sample
-                            # (utils.py:116): checked on the device, next to the PCM that is there anyway
-                            monos = engine.upload(plan_a, [np.asarray(audios[i].samples, dtype=np.float32) for i, _ in cand])
-                            flags = torch.zeros(len(cand), dtype=torch.int32, device=batch.pcm.device)
+                            # (utils.py:116): two 64-bit sums over the bit patterns, formed on the device from the stereo PCM
+                            # that is there anyway and on the host from the mono samples (numpy releases the GIL)
+                            fps = torch.zeros(2 * len(cand), dtype=torch.int64, device=batch.pcm.device)
                             st_ptr = C.c_void_p(torch.cuda.current_stream(dev_index).cuda_stream)
                             for j in range(len(cand)):
-                                nat.check(plan_a.lib.ta_mono_mix_check(
-                                    C.c_void_p(batch.pcm.data_ptr() + 4 * int(batch.offsets[j])),
-                                    C.c_void_p(monos.pcm.data_ptr() + 4 * int(monos.offsets[j])), int(batch.n_samples[j]),
-                                    C.c_void_p(flags.data_ptr() + 4 * j), st_ptr))
-                            ok = [v == 0 for v in flags.cpu().tolist()]
-                            del monos
+                                nat.check(plan_a.lib.ta_mono_mix_fingerprint(
+                                    C.c_void_p(batch.pcm.data_ptr() + 4 * int(batch.offsets[j])), int(batch.n_samples[j]),
+                                    C.c_void_p(fps.data_ptr() + 16 * j), st_ptr))
+                            dev_fp = fps.cpu().numpy().view(np.uint64).reshape(-1, 2)
+                            ok = [tuple(int(v) for v in dev_fp[j]) == host_fp[j].result() for j in range(len(cand))]
                         if not all(ok):   # rare: re-upload only the consistent tracks, the others take the single-track path
                             bad += [ic for ic, o in zip(cand, ok) if not o]
                             cand = [ic for ic, o in zip(cand, ok) if o]
