@@ -532,7 +532,7 @@ def ours(args, rank, world, local_rank):
         achieved = k1_bytes / (stage[0] * 1e-3) / 1e9
         traffic = None  # DRAM bytes of one K1 launch from the committed ncu --set full capture of this same command
         try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r1_k1_traffic.json")))
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r2_k1_traffic.json")))
             if args.tracks_per_gpu == 128 and args.seconds == 180.0:
                 traffic = tj["traffic_bytes"]
         except Exception:

@@ -250,6 +250,13 @@ TA_API int ta_chroma_cqt(const ta_plan* plan, const ta_batch* batch, const float
                          float* chroma_cqt, float* cqt_mag, double* cqt_tuning, void* cqt_scratch, size_t cqt_scratch_bytes,
                          void* workspace, size_t workspace_bytes, void* stream);
 
+/* K9 with the component matrices themselves: harmonic, percussive = librosa.decompose.hpss(magnitude) ([B * P] floats each,
+ * laid out like the magnitude) next to their per-frame sums.  For callers that run the reference's own analyse_structure
+ * (analysis/structure.py:52, 135-144, 212-213) on the result; the fused schedule only ever needs the sums. */
+TA_API int ta_hpss_components(const ta_plan* plan, const ta_batch* batch, const float* magnitude, float* scratch, float* harmonic,
+                              float* percussive, float* harmonic_sum, float* percussive_sum, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* K4b: windowed (tempogram_win frames, Hann, centred, inf-normalised) autocorrelation of the onset
  * envelope: librosa.feature.tempogram at report.py:260.  Output rows = lags, (win, T_i) per track. */
 TA_API int ta_tempogram(const ta_plan* plan, const ta_batch* batch, const float* onset_env, float* tempogram,

@@ -9,8 +9,8 @@ sr = 44_100
 plan = runtime.get_plan(sr)
 x = synth.synth_track(synth.DEFAULT_SEED, 180.0, sr, 2)
 batch = engine.upload(plan, [x] * 32)
-bufs = engine.FrontendBuffers(batch, engine.ALL_OUTPUTS)
-for _ in range(3):
+bufs = engine.FrontendBuffers(batch, tuple(o for o in engine.ALL_OUTPUTS if o != "cqt_mag"))
+for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
     engine.run_device(plan, batch, bufs)
 torch.cuda.synchronize()
 print("ok", engine.launch_count())

@@ -15,6 +15,7 @@ WANT = [
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%", None),
     ("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "fma%", None),
     ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64%", None),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%", None),
     ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%", None),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.avg.pct_of_peak_sustained_elapsed", "smem_wf%", None),
     ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%", None),

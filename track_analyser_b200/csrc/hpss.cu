@@ -144,9 +144,13 @@ __global__ void __launch_bounds__(32 * HT_WARPS) hpss_time_median_kernel(const T
 // divisions (<= 2 ulp from the reference's float32 masks; the outputs are sums of ~1000 masked magnitudes).
 static constexpr int HF_THREADS = 128;
 
+// FULL: also store the two component matrices S * mask_h and S * mask_p ((bins, T) like the magnitude): what
+// librosa.decompose.hpss returns, for callers that run the reference's own analyse_structure on it (compat/).
+template <bool FULL>
 __global__ void __launch_bounds__(HF_THREADS) hpss_freq_median_kernel(const TrackDesc* __restrict__ tracks,
                                                                       const float* __restrict__ mag, const float* __restrict__ harm,
                                                                       float* __restrict__ harm_sum, float* __restrict__ perc_sum,
+                                                                      float* __restrict__ harm_full, float* __restrict__ perc_full,
                                                                       int n_bins, float one) {
     __shared__ float ring_all[32 * HF_THREADS];
     const TrackDesc td = tracks[blockIdx.y];
@@ -209,6 +213,11 @@ __global__ void __launch_bounds__(HF_THREADS) hpss_freq_median_kernel(const Trac
                 }
                 ph = fmaf(sv, mh, ph);
                 pp = fmaf(sv, mp, pp);
+                if (FULL) {
+                    const size_t o = size_t(td.pitch_off) * n_bins + size_t(k) * ld + t;
+                    harm_full[o] = sv * mh;
+                    perc_full[o] = sv * mp;
+                }
                 // bin k-15 (mirrored below bin 0) leaves, bin k+16 enters
                 const int lo = (k >= HH) ? k - HH : HH - 1 - k;
                 const float old = ring[(lo & 31) * HF_THREADS];
@@ -225,7 +234,7 @@ __global__ void __launch_bounds__(HF_THREADS) hpss_freq_median_kernel(const Trac
 }
 
 int run_hpss(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_tracks, const float* mag, float* scratch,
-             float* harm_sum, float* perc_sum, cudaStream_t stream) {
+             float* harm_sum, float* perc_sum, cudaStream_t stream, float* harm_full, float* perc_full) {
     TA_REQUIRE(mag && scratch && harm_sum && perc_sum, "hpss needs magnitude, hpss_scratch and both sum outputs");
     TA_REQUIRE(hb.n_tracks <= 65535, "at most 65535 tracks per call");
     const int B = plan->n_bins;
@@ -237,7 +246,10 @@ int run_hpss(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_tracks
     TA_CUDA(cudaGetLastError());
     TA_REQUIRE(B >= 32, "hpss needs at least 32 frequency bins");
     dim3 g2((hb.max_frames + HF_THREADS - 1) / HF_THREADS, hb.n_tracks);
-    hpss_freq_median_kernel<<<g2, HF_THREADS, 0, stream>>>(d_tracks, mag, scratch, harm_sum, perc_sum, B, 1.0f);
+    if (harm_full && perc_full)
+        hpss_freq_median_kernel<true><<<g2, HF_THREADS, 0, stream>>>(d_tracks, mag, scratch, harm_sum, perc_sum, harm_full, perc_full, B, 1.0f);
+    else
+        hpss_freq_median_kernel<false><<<g2, HF_THREADS, 0, stream>>>(d_tracks, mag, scratch, harm_sum, perc_sum, nullptr, nullptr, B, 1.0f);
     count_launch();
     TA_CUDA(cudaGetLastError());
     return TA_OK;

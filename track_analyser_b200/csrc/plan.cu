@@ -294,7 +294,7 @@ int run_tempogram(const ta_plan*, const HostBatch&, const TrackDesc*, const floa
 int run_mfcc(const ta_plan*, const HostBatch&, const TrackDesc*, const float* mel, const uint32_t* mel_max, double* mfcc,
              cudaStream_t);
 int run_hpss(const ta_plan*, const HostBatch&, const TrackDesc*, const float* mag, float* scratch, float* harm_sum, float* perc_sum,
-             cudaStream_t);
+             cudaStream_t, float* harm_full = nullptr, float* perc_full = nullptr);
 int run_self_similarity(const ta_plan*, const HostBatch&, const TrackDesc*, const double* mfcc, double* scratch, double* out,
                         cudaStream_t);
 
@@ -563,6 +563,18 @@ int ta_chroma_cqt(const ta_plan* plan, const ta_batch* batch, const float* magni
     if (rc != TA_OK) return rc;
     return run_chroma_cqt(plan, hb, ws.d_tracks, magnitude, frame_max, chroma_cqt, cqt_mag, cqt_tuning, cqt_scratch,
                           cqt_scratch_bytes_, st);
+}
+
+int ta_hpss_components(const ta_plan* plan, const ta_batch* batch, const float* magnitude, float* scratch, float* harmonic,
+                       float* percussive, float* harmonic_sum, float* percussive_sum, void* workspace, size_t workspace_bytes,
+                       void* stream) {
+    TA_REQUIRE(harmonic && percussive, "harmonic / percussive must not be NULL");
+    HostBatch hb;
+    Workspace ws;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = prepare(plan, batch, workspace, workspace_bytes, st, hb, ws);
+    if (rc != TA_OK) return rc;
+    return run_hpss(plan, hb, ws.d_tracks, magnitude, scratch, harmonic_sum, percussive_sum, st, harmonic, percussive);
 }
 
 uint64_t ta_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
