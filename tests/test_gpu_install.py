@@ -71,12 +71,15 @@ def test_reference_analyse_track_runs_on_the_kernels_and_agrees_with_the_mirror(
     assert out["bpm"][0] == pytest.approx(out["bpm"][1], rel=1e-9) and out["beats"][0] == out["beats"][1]
     assert out["downbeats"][0] == out["downbeats"][1]
     assert out["seg"][0] == out["seg"][1] and out["novelty"] < 1e-9
-    for k in ("lufs", "tp", "rms", "lra"):
+    for k in ("lufs", "rms", "lra"):
         assert out[k][0] == pytest.approx(out[k][1], abs=1e-6), k
+    # the reference takes max|.| of the float32 signal the resampy shim returns; the mirror's kernel keeps the peak in float64
+    assert out["tp"][0] == pytest.approx(out["tp"][1], abs=1e-4)
     assert out["key"][0] == out["key"][1] and out["key2"][0] == out["key2"][1] and out["chords"][0] == out["chords"][1]
     assert out["balance"][0] == pytest.approx(out["balance"][1], rel=1e-6)
     assert out["ltas"] < 1e-6 and out["centroid"] < 1e-6 and out["rolloff"]
-    assert out["stereo"][0] == pytest.approx(out["stereo"][1], rel=1e-6, abs=1e-9)
+    # np.corrcoef on float32 mid / side (stereo.py:60-66) against the kernel's float64 moments: float32 rounding apart
+    assert out["stereo"][0] == pytest.approx(out["stereo"][1], rel=1e-5, abs=1e-9)
 
 
 def test_reference_test_suite_passes_on_the_kernels():

@@ -34,7 +34,7 @@ _registry: dict = {}   # id(array) -> (weakref to the array, TrackResult, sample
 
 def _remember(arr: np.ndarray, res, sr: int, n_fft: int, hop: int) -> np.ndarray:
     try:
-        _registry[id(arr)] = (weakref.ref(arr, lambda _r, k=id(arr): _registry.pop(k, None)), res, sr, n_fft, hop)
+        _registry[id(arr)] = (weakref.ref(arr, lambda _r, k=id(arr), reg=_registry: reg.pop(k, None)), res, sr, n_fft, hop)
     except TypeError:  # pragma: no cover - not weak-referenceable
         pass
     return arr
@@ -143,6 +143,15 @@ def frames_to_time(frames, *, sr=22_050, hop_length=512, n_fft=None):
 
 def time_to_frames(times, *, sr=22_050, hop_length=512, n_fft=None):
     return hostlogic.time_to_frames(times, sr, hop_length)
+
+
+def midi_to_hz(notes):
+    """librosa.midi_to_hz (the reference's tests build their chords with it): 440 * 2^((m - 69) / 12)."""
+    return 440.0 * (2.0 ** ((np.asanyarray(notes) - 69.0) / 12.0))
+
+
+def hz_to_midi(frequencies):
+    return 12.0 * (np.log2(np.asanyarray(frequencies)) - np.log2(440.0)) + 69.0
 
 
 def tempo_frequencies(n_bins, *, hop_length=512, sr=22_050):
@@ -344,7 +353,7 @@ def build_shims() -> dict:
                       chroma_stft=chroma_stft, chroma_cqt=chroma_cqt, melspectrogram=melspectrogram, mfcc=mfcc, rms=rms,
                       tempogram=tempogram)
     decompose = _module("librosa.decompose", hpss=hpss)
-    librosa = _module("librosa", stft=stft, fft_frequencies=fft_frequencies, frames_to_time=frames_to_time,
+    librosa = _module("librosa", stft=stft, midi_to_hz=midi_to_hz, hz_to_midi=hz_to_midi, fft_frequencies=fft_frequencies, frames_to_time=frames_to_time,
                       time_to_frames=time_to_frames, tempo_frequencies=tempo_frequencies, autocorrelate=autocorrelate,
                       resample=resample, power_to_db=power_to_db, amplitude_to_db=amplitude_to_db, util=util, onset=onset,
                       feature=feature, decompose=decompose, __version__="0.10.2.post1+ta_b200")

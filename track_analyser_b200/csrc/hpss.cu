@@ -174,7 +174,9 @@ __global__ void __launch_bounds__(HF_THREADS) hpss_freq_median_kernel(const Trac
         const int e = k + HH + 1;
         return __ldg(S + size_t(e < n_bins ? e : 2 * n_bins - e - 1) * ld);
     };
-    double acc_h = 0.0, acc_p = 0.0;
+    // np.sum(harmonic, axis=0) as numpy evaluates it on the float32 component matrices (structure.py:212-213): the products
+    // S * mask rounded to float32, added row after row in float32 -- a sequential chain per frame, which is this thread's walk
+    float acc_h = 0.f, acc_p = 0.f;
     float nv[4], hv[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -193,7 +195,6 @@ __global__ void __launch_bounds__(HF_THREADS) hpss_freq_median_kernel(const Trac
                 hv[u] = __ldg(H + size_t(k) * ld);
             }
         }
-        float ph = 0.f, pp = 0.f;
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int k = k0 + u;
@@ -211,12 +212,13 @@ __global__ void __launch_bounds__(HF_THREADS) hpss_freq_median_kernel(const Trac
                     mh = a * r;
                     mp = b * r;
                 }
-                ph = fmaf(sv, mh, ph);
-                pp = fmaf(sv, mp, pp);
+                const float hk = __fmul_rn(sv, mh), pk = __fmul_rn(sv, mp);
+                acc_h = __fadd_rn(acc_h, hk);
+                acc_p = __fadd_rn(acc_p, pk);
                 if (FULL) {
                     const size_t o = size_t(td.pitch_off) * n_bins + size_t(k) * ld + t;
-                    harm_full[o] = sv * mh;
-                    perc_full[o] = sv * mp;
+                    harm_full[o] = hk;
+                    perc_full[o] = pk;
                 }
                 // bin k-15 (mirrored below bin 0) leaves, bin k+16 enters
                 const int lo = (k >= HH) ? k - HH : HH - 1 - k;
@@ -226,11 +228,9 @@ __global__ void __launch_bounds__(HF_THREADS) hpss_freq_median_kernel(const Trac
                 window_replace(w, old, cv[u], one);
             }
         }
-        acc_h += double(ph);
-        acc_p += double(pp);
     }
-    harm_sum[td.pitch_off + t] = float(acc_h);
-    perc_sum[td.pitch_off + t] = float(acc_p);
+    harm_sum[td.pitch_off + t] = acc_h;
+    perc_sum[td.pitch_off + t] = acc_p;
 }
 
 int run_hpss(const ta_plan* plan, const HostBatch& hb, const TrackDesc* d_tracks, const float* mag, float* scratch,
