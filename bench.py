@@ -297,8 +297,11 @@ def verify_one_track(plan, x, res):
 
     mono = np.mean(x, axis=0)
     mag = np.abs(olr.stft(mono, n_fft=N_FFT, hop_length=HOP))
-    ok = np.abs(res["magnitude"] - mag) <= 1e-6 + 1e-4 * mag
-    checks = {"magnitude": bool(ok.size - int(ok.sum()) <= max(1, int(1e-6 * ok.size)))}
+    # rtol 1e-4 / atol 1e-6 per bin; the few bins 1e4 below their frame's peak that miss it must sit inside the float32
+    # transform's own rounding floor (4 eps32 of the frame maximum: the oracle's float32 FFT is no closer to a float64 one)
+    err = np.abs(res["magnitude"] - mag)
+    ok = (err <= 1e-6 + 1e-4 * mag) | (err <= 4.0 * np.finfo(np.float32).eps * np.max(mag, axis=0, keepdims=True))
+    checks = {"magnitude": bool(ok.all()) and bool(np.mean(err <= 1e-6 + 1e-4 * mag) >= 0.99999)}
     mel = np.einsum("ft,mf->mt", mag**2, olr.filters_mel(SR, N_FFT, n_mels=N_MELS), optimize=True)
     env = olr.onset_strength(S=olr.power_to_db(mel), sr=SR, hop_length=HOP)
     close = lambda a, b: bool(np.allclose(a, b, rtol=1e-4, atol=1e-6))  # noqa: E731

@@ -16,7 +16,7 @@
 //             epilogue    (a) magnitude tile -> global, row segments of TF contiguous floats;
 //                             per-bin time sums (LTAS, |mid|^2), one thread per bin
 //                         (b) sparse Slaney mel projection of tile^2 -> global (two frames per thread)
-//                         (c) per-frame centroid / max: one warp per frame pair, one bin chunk per lane
+//                         (c) per-frame centroid / max / sum from partial sums taken during (a)'s walk
 //                             (the roll-off bin is an exact sequential float32 chain: chroma.cu walks it)
 // Algorithmic HBM bytes per tile: read C*TF*hop*4 (PCM), write (B+M)*TF*4 + 16*TF.
 #pragma once
@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
         const TrackDesc td = p.tracks[trk];
         const int t0 = (w - td.tile_begin) * TF;
         const int nf = min(TF, td.n_frames - t0);
+        const bool want_feat = p.centroid || p.frame_max || p.frame_sum;
 
         // ------------------------------ FFT phase ------------------------------
         // Every slot of the tile is transformed, frames past the end of the track as zeros, so the
@@ -321,19 +322,64 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
         __syncthreads();
 
         // ------------------------------ epilogue ------------------------------
-        {   // (a) magnitude rows -> global (64-bit stores, TF contiguous floats per row).  A half-warp reads RPH rows
-            // that are D rows apart so that its 16 64-bit words fall into 16 distinct bank pairs.
-            constexpr int RPH = 16 / HP, D = (TF == 16) ? 8 : (TF == 8) ? 4 : 1, RB = D * RPH;
+        {   // (a) one walk over the tile: magnitude rows -> global (64-bit stores, TF contiguous floats per row) and, on
+            // the way, this thread's share of the per-frame sums of (c).  A half-warp reads RPH rows that are DR rows
+            // apart so that its 16 64-bit words fall into 16 distinct bank pairs; a thread keeps its frame pair and
+            // steps KS rows at a time.
+            constexpr int RPH = 16 / HP, DR = (TF == 16) ? 8 : (TF == 8) ? 4 : 1, RB = DR * RPH, KS = (S::THREADS / 16 / DR) * RB;
             const int hw = tid >> 4, l16 = tid & 15, fp = l16 % HP, ri = l16 / HP;
-            const bool ok0 = 2 * fp < nf, ok1 = 2 * fp + 1 < nf;
-            if (p.mag) {
-                float* dst = p.mag + size_t(td.pitch_off) * B + t0 + 2 * fp;
-                for (int q = hw; (q / D) * RB < B; q += S::THREADS / 16) {
-                    const int k = (q / D) * RB + (q % D) + ri * D;
-                    if (k < B && ok0) {
-                        const float2 a = *reinterpret_cast<const float2*>(tile + k * TFP + 2 * fp);
-                        if (ok1) *reinterpret_cast<float2*>(dst + size_t(k) * td.ld) = a;
-                        else dst[size_t(k) * td.ld] = a.x;
+            const int k0 = (hw / DR) * RB + (hw % DR) + ri * DR;
+            if (p.mag || want_feat) {
+                const float* src = tile + k0 * TFP + 2 * fp;
+                float2 s1 = make_float2(0.f, 0.f), s2 = s1, mx = s1;
+                float kf = float(k0);
+                auto take = [&](const float2 a) {
+                    s1 = padd(s1, a);
+                    s2 = pfmas(a, kf, s2);
+                    mx.x = fmaxf(mx.x, a.x);
+                    mx.y = fmaxf(mx.y, a.y);
+                    kf += float(KS);
+                };
+                if (p.mag) {
+                    float* dst = p.mag + size_t(td.pitch_off) * B + size_t(k0) * td.ld + t0 + 2 * fp;
+                    const size_t dstep = size_t(KS) * td.ld;
+                    if (nf == TF) {
+#pragma unroll 4
+                        for (int k = k0; k < B; k += KS, src += KS * TFP, dst += dstep) {
+                            const float2 a = *reinterpret_cast<const float2*>(src);
+                            *reinterpret_cast<float2*>(dst) = a;
+                            take(a);
+                        }
+                    } else {
+                        const bool ok0 = 2 * fp < nf, ok1 = 2 * fp + 1 < nf;
+                        for (int k = k0; k < B; k += KS, src += KS * TFP, dst += dstep) {
+                            const float2 a = *reinterpret_cast<const float2*>(src);
+                            if (ok1) *reinterpret_cast<float2*>(dst) = a;
+                            else if (ok0) dst[0] = a.x;
+                            take(a);
+                        }
+                    }
+                } else {
+#pragma unroll 4
+                    for (int k = k0; k < B; k += KS, src += KS * TFP) take(*reinterpret_cast<const float2*>(src));
+                }
+                if (want_feat) {
+                    // the 32 / HP lanes of a warp that share a frame pair, then one slot per (warp, frame pair) in the
+                    // exchange area of the last transform group (idle until the next tile's pass 1)
+#pragma unroll
+                    for (int o = HP; o < 32; o <<= 1) {
+                        s1.x += __shfl_xor_sync(0xffffffffu, s1.x, o);
+                        s1.y += __shfl_xor_sync(0xffffffffu, s1.y, o);
+                        s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o);
+                        s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+                        mx.x = fmaxf(mx.x, __shfl_xor_sync(0xffffffffu, mx.x, o));
+                        mx.y = fmaxf(mx.y, __shfl_xor_sync(0xffffffffu, mx.y, o));
+                    }
+                    if (lane < HP) {
+                        float2* pp = reinterpret_cast<float2*>(ex_all + size_t(NG - 1) * E::SLOTS) + (warp * HP + lane) * 3;
+                        pp[0] = s1;
+                        pp[1] = s2;
+                        pp[2] = mx;
                     }
                 }
             }
@@ -380,52 +426,31 @@ __global__ void __launch_bounds__(512, 1) stft_fused_kernel(const StftParams p) 
                 if (lane == 0) atomicMax(&p.mel_max[trk], __float_as_uint(vmax));
             }
         }
-        // (c) per-frame centroid / max: warp per frame pair, lane c owns bins [c*CH, c*CH+CH).
-        // fp32 chunk sums s1 = sum |X|, s2 = sum (k-kb)|X|; centroid = df * sum_c (s2_c + kb_c*s1_c) / sum_c s1_c
-        // combined in double.  (librosa rounds |X|/sum to float32 before the float64 dot product; that changes
-        // the result by ~2e-9 relative.)
-        if (p.centroid || p.frame_max || p.frame_sum) {
-            for (int fp = warp; 2 * fp < nf; fp += S::THREADS / 32) {   // warp per frame PAIR: one 64-bit read serves both
-                const float* col = tile + 2 * fp;
-                const int kb = lane * CH, ke = min(kb + CH, B);
-                float2 q1 = make_float2(0.f, 0.f), q2 = q1, q3 = q1;
-                float kf = 0.f;
-                for (int k = kb; k < ke; ++k) {
-                    const float2 a = *reinterpret_cast<const float2*>(col + k * TFP);
-                    q1 = padd(q1, a);
-                    q2 = pfmas(a, kf, q2);
-                    q3.x = fmaxf(q3.x, a.x);
-                    q3.y = fmaxf(q3.y, a.y);
-                    kf += 1.0f;
-                }
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int f = 2 * fp + h;
-                    if (f >= nf) break;  // warp-uniform
-                    const float s1 = h ? q1.y : q1.x, s2 = h ? q2.y : q2.x;
-                    float s3 = h ? q3.y : q3.x;
-                    if (p.centroid || p.frame_sum) {
-                        double den = double(s1), num = double(s2) + double(kb) * double(s1);
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            den += __shfl_xor_sync(0xffffffffu, den, o);
-                            num += __shfl_xor_sync(0xffffffffu, num, o);
-                        }
-                        if (lane == 0) {
-                            const double df = p.freqs[1];
-                            if (p.centroid) p.centroid[col_out(td, t0, f)] = (den < 1.1754943508222875e-38) ? df * num : df * num / den;
-                            if (p.frame_sum) p.frame_sum[col_out(td, t0, f)] = float(den);
-                        }
-                    }
-                    if (p.frame_max) {
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) s3 = fmaxf(s3, __shfl_xor_sync(0xffffffffu, s3, o));
-                        if (lane == 0) p.frame_max[col_out(td, t0, f)] = s3;
-                    }
-                }
-            }
-        }
         __syncthreads();
+        // (c) per-frame centroid / max / sum: the 16 warps' partial sums s1 = sum |X|, s2 = sum k |X| (float32 over the <= 17
+        // rows a thread walked and its 32 / HP lanes) combined in double, in warp order, by one thread per frame:
+        // centroid = df * s2 / s1.  (librosa rounds |X| / sum to float32 before the float64 dot product; that changes
+        // the result by ~2e-9 relative.)
+        if (want_feat && g == NG - 1) {
+            if (r < nf) {
+                const float* part = reinterpret_cast<const float*>(ex_all + size_t(NG - 1) * E::SLOTS);
+                const int fp = r >> 1, h = r & 1;
+                double den = 0.0, num = 0.0;
+                float m = 0.f;
+#pragma unroll 4
+                for (int w = 0; w < S::THREADS / 32; ++w) {
+                    const float* pp = part + (w * HP + fp) * 6;
+                    den += double(pp[h]);
+                    num += double(pp[2 + h]);
+                    m = fmaxf(m, pp[4 + h]);
+                }
+                const double df = p.freqs[1];
+                if (p.centroid) p.centroid[col_out(td, t0, r)] = (den < 1.1754943508222875e-38) ? df * num : df * num / den;
+                if (p.frame_sum) p.frame_sum[col_out(td, t0, r)] = float(den);
+                if (p.frame_max) p.frame_max[col_out(td, t0, r)] = m;
+            }
+            group_barrier(g, M);   // the partial sums are read before this group's next pass 1 overwrites them
+        }
     }
     flush(trk);
 }
