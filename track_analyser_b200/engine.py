@@ -268,10 +268,11 @@ _pack_pool = None
 _COPY_PIECE = 2 << 20   # floats per host-to-device copy (8 MB)
 
 
-def upload(plan: Plan, tracks: Sequence[np.ndarray]) -> DeviceBatch:
-    """Host tracks -> one flat device buffer.  A track that already sits in pinned memory is copied from where it is;
-    pageable ones go through the process-wide pinned staging buffer, filled by a few threads (numpy's copy releases the
-    GIL and one core moves ~12 GB/s, a fifth of what the link takes)."""
+def upload(plan: Plan, tracks: Sequence[np.ndarray], out: "torch.Tensor | None" = None) -> DeviceBatch:
+    """Host tracks -> one flat device buffer (``out`` if it is a float32 tensor on the plan's device that is large enough,
+    else a new one).  A track that already sits in pinned memory is copied from where it is; pageable ones go through the
+    process-wide pinned staging buffer, filled by a few threads (numpy's copy releases the GIL and one core moves
+    ~12 GB/s, a fifth of what the link takes)."""
     global _pack_pool
     tracks = [np.asarray(t, dtype=np.float32) for t in tracks]
     chans = {1 if t.ndim == 1 else t.shape[0] for t in tracks}
@@ -282,7 +283,10 @@ def upload(plan: Plan, tracks: Sequence[np.ndarray]) -> DeviceBatch:
     sizes = (channels * n_samples + 3) & ~3
     offsets = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
     total = int(sizes.sum())
-    dev = torch.empty(max(total, 4), dtype=torch.float32, device=f"cuda:{plan.device}")
+    if out is not None and out.dtype == torch.float32 and out.is_cuda and out.device.index == plan.device and out.numel() >= max(total, 4):
+        dev = out[: max(total, 4)]
+    else:
+        dev = torch.empty(max(total, 4), dtype=torch.float32, device=f"cuda:{plan.device}")
     flat = [torch.from_numpy(t.reshape(-1)) if t.flags.c_contiguous else None for t in tracks]
     pinned = [f is not None and f.numel() > 0 and f.is_pinned() for f in flat]
     with _staging_lock:  # one process-wide pinned staging buffer: fill, copy, and wait before anyone refills it

@@ -204,18 +204,19 @@ def _stage_worker(task):
 
 
 def _mono_fingerprint(mono) -> tuple:
-    """(sum of the float32 bit patterns, sum of bit pattern * ((i & 0xffff) + 1)) modulo 2^64: what
-    ``ta_mono_mix_fingerprint`` forms on the device from the stereo pair."""
+    """(sum of the float32 bit patterns, sum of bit pattern * ((i & 0xffff) + 1)) modulo 2^32: the low halves of what
+    ``ta_mono_mix_fingerprint`` forms on the device from the stereo pair.  All sums stay in uint32 (they wrap, which is the
+    modulus): numpy then adds at memory speed instead of casting every sample to 64 bits."""
     b = np.ascontiguousarray(mono, dtype=np.float32).view(np.uint32)
     n = b.shape[0]
     m = n // 65536
-    col = np.zeros(65536, dtype=np.uint64)
-    if m:
-        col += b[: m * 65536].reshape(m, 65536).sum(axis=0, dtype=np.uint64)
-    col[: n - m * 65536] += b[m * 65536:]
+    col = np.zeros(65536, dtype=np.uint32)
     with np.errstate(over="ignore"):
-        s1 = int(col.sum(dtype=np.uint64))
-        s2 = int((col * np.arange(1, 65537, dtype=np.uint64)).sum(dtype=np.uint64))
+        if m:
+            col += np.add.reduce(b[: m * 65536].reshape(m, 65536), axis=0, dtype=np.uint32)
+        col[: n - m * 65536] += b[m * 65536:]
+        s1 = int(np.add.reduce(col, dtype=np.uint32))
+        s2 = int(np.add.reduce(col * np.arange(1, 65537, dtype=np.uint32), dtype=np.uint32))
     return s1, s2
 
 
@@ -326,12 +327,31 @@ def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] 
         chunks += [(sr, ch, idxs[c0: c0 + chunk_tracks]) for c0 in range(0, len(idxs), chunk_tracks)]
 
     uploaded: "queue.Queue" = queue.Queue(maxsize=2)
+    # device PCM buffers go round between the two threads (at most four exist: one being filled, two queued, one in use)
+    # instead of being allocated per chunk: a buffer comes back once the kernels that read it have finished
+    pcm_free: "queue.Queue" = queue.Queue()
+    pcm_made = [0]
+
+    def pcm_buffer(n_floats: int):
+        while True:
+            try:
+                buf = pcm_free.get(block=pcm_made[0] >= 4)
+            except queue.Empty:
+                buf = None
+            if buf is not None and buf.numel() >= n_floats:
+                return buf
+            if buf is not None:
+                pcm_made[0] -= 1   # too small for this chunk: let it go
+                continue
+            pcm_made[0] += 1
+            return torch.empty(n_floats, dtype=torch.float32, device=f"cuda:{dev_index}")
 
     def uploader():
         try:
             stream = torch.cuda.Stream(dev_index)
             with cf.ThreadPoolExecutor(max_workers=8) as tp, torch.cuda.stream(stream):
                 for sr, ch, idxs in chunks:
+                    _u = [time.perf_counter()]
                     cand, bad = [], []
                     for i in idxs:
                         c = _batch_buffer(audios[i])
@@ -341,7 +361,10 @@ def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] 
                         plan_a = runtime.get_plan(sr, *_PLAN_A, device=device)
                         # (the host half of the fingerprints runs in the pool while the PCM travels)
                         host_fp = [tp.submit(_mono_fingerprint, audios[i].samples) for i, _ in cand] if ch == 2 else []
-                        batch = engine.upload(plan_a, [c[0] for _, c in cand])
+                        need = sum((c[0].size + 3) & ~3 for _, c in cand)
+                        buf = pcm_buffer(max(need, 4))
+                        batch = engine.upload(plan_a, [c[0] for _, c in cand], out=buf)
+                        _u.append(time.perf_counter())
                         ok = [True] * len(cand)
                         if ch == 2:
                             # one stereo run may serve the mono stages only if mono == mean(stereo) sample for sample
@@ -354,25 +377,36 @@ def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] 
                                     C.c_void_p(batch.pcm.data_ptr() + 4 * int(batch.offsets[j])), int(batch.n_samples[j]),
                                     C.c_void_p(fps.data_ptr() + 16 * j), st_ptr))
                             dev_fp = fps.cpu().numpy().view(np.uint64).reshape(-1, 2)
-                            ok = [tuple(int(v) for v in dev_fp[j]) == host_fp[j].result() for j in range(len(cand))]
+                            ok = [tuple(int(v) & 0xffffffff for v in dev_fp[j]) == host_fp[j].result() for j in range(len(cand))]
                         if not all(ok):   # rare: re-upload only the consistent tracks, the others take the single-track path
                             bad += [ic for ic, o in zip(cand, ok) if not o]
                             cand = [ic for ic, o in zip(cand, ok) if o]
-                            batch = engine.upload(plan_a, [c[0] for _, c in cand]) if cand else None
+                            batch = engine.upload(plan_a, [c[0] for _, c in cand], out=buf) if cand else None
+                            if batch is None:
+                                pcm_free.put(buf)
                         good = [(i, c[0]) for i, c in cand]
-                        if batch is not None:
-                            batch.pcm.record_stream(main_stream)
                     bad = [i for i, _ in bad]
+                    _u.append(time.perf_counter())
                     uploaded.put((sr, ch, good, bad, batch))
+                    if trace:
+                        _u.append(time.perf_counter())
+                        print("[ta uploader] upload %.1f, fingerprints %.1f, queue %.1f ms"
+                              % tuple(1e3 * (b - a) for a, b in zip(_u, _u[1:])), file=sys.stderr)
             uploaded.put(None)
         except BaseException as exc:  # noqa: BLE001 - handed to the consuming thread
             uploaded.put(exc)
 
+    import gc
+
+    gc_was_on = gc.isenabled() and not os.environ.get("TA_KEEP_GC")
+    if gc_was_on:
+        gc.disable()   # a generation-2 pass over the unpickled results stops every thread of this process for ~0.1 s
     th = threading.Thread(target=uploader, daemon=True)
     th.start()
     if _ring is None:
         _ring = _ShmRing()
     ring, pending = _ring, []   # pending: (futures, indices, slot)
+    buffers: dict = {}
     free_slots = list(range(ring.slots))
 
     def collect(entry):
@@ -408,7 +442,14 @@ def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] 
                          ("moments", "band_energy")))
         launched = []
         for key, plan, bt, outs in runs:
-            bufs = engine.FrontendBuffers(bt, outs)
+            # output buffers are reused by the next chunk of the same geometry (this thread waits for the copies below
+            # before it takes another chunk), which saves ~30 allocations per chunk
+            bkey = (key, bt.n_samples.tobytes(), outs)
+            bufs = buffers.get(bkey)
+            if bufs is None:
+                while len(buffers) >= 3:   # the runs of one chunk; a chunk of another geometry replaces them
+                    buffers.pop(next(iter(buffers)))
+                bufs = buffers[bkey] = engine.FrontendBuffers(bt, outs)
             engine.run_device(plan, bt, bufs)
             launched.append((key, plan, bt, bufs))
         # every requested output array of the batch goes to one slot of the shared-memory ring with one copy each; the
@@ -434,6 +475,7 @@ def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] 
                 dst = np.ndarray(shape, dtype=dtype, buffer=ring.mm, offset=base + off)
                 torch.from_numpy(dst).copy_(bufs.t[name], non_blocking=True)
         main_stream.synchronize()
+        pcm_free.put(batch.pcm._base if batch.pcm._base is not None else batch.pcm)   # the whole buffer, not the slice in use
         del launched, batch
         _t.append(time.perf_counter())
         tasks = []
@@ -448,7 +490,11 @@ def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] 
         if trace:
             print("[ta analyse_tracks] chunk of %d: wait for upload %.1f, kernels + copy to shm %.1f, submit %.1f ms"
                   % ((len(good),) + tuple(1e3 * (b - a) for a, b in zip(_t, _t[1:]))), file=sys.stderr)
-    for entry in pending:
-        collect(entry)
-    th.join()
+    try:
+        for entry in pending:
+            collect(entry)
+        th.join()
+    finally:
+        if gc_was_on:
+            gc.enable()
     return results
