@@ -1,6 +1,8 @@
 """The boundary beyond the default configuration: every power-of-two n_fft from 256 to 4096, any hop,
 other analysis windows, other true-peak oversampling factors, and the host-buffer C-ABI entry point.  Run with -m gpu."""
 
+import os
+
 import numpy as np
 import pytest
 
@@ -100,3 +102,22 @@ def test_host_buffer_entry_point_equals_the_device_path():
     np.testing.assert_array_equal(c["onset_env"], a[0]["onset_env"])
     np.testing.assert_array_equal(c["chroma"], a[0]["chroma"])
     assert c["lufs"] == pytest.approx(a[0]["lufs"], abs=1e-9)
+
+
+def test_the_ctypes_stub_printed_in_integration_md_runs_as_printed():
+    """the numpy-only stub over ta_frontend_run_host, executed verbatim (library path aside)."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(# src/track_analyser/_b200\.py.*?)```", text, re.S).group(1)
+    block = block.replace('C.CDLL("libta_b200.so")', "C.CDLL(%r)" % os.path.join(root, "track_analyser_b200", "libta_b200.so"))
+    ns: dict = {}
+    exec(compile(block, "INTEGRATION.md", "exec"), ns)
+    sr = 22_050
+    y = synth.synth_track(77, 4.0, sr, 1).reshape(-1)
+    mag, env = ns["stft_magnitude_and_onsets"](y, sr)
+    ref = np.abs(olr.stft(y, n_fft=2048, hop_length=512))
+    _magnitude_close(mag, ref, 2048)
+    mel = np.einsum("ft,mf->mt", ref**2, olr.filters_mel(sr, 2048, n_mels=128), optimize=True)
+    np.testing.assert_allclose(env, olr.onset_strength(S=olr.power_to_db(mel), sr=sr, hop_length=512), rtol=RTOL, atol=ATOL)
