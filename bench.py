@@ -289,6 +289,38 @@ def pcie_probe(dev, nbytes=1 << 30, reps=3):
     return out
 
 
+def pcie_sustained(dev, up_bytes, down_bytes, reps, barrier):
+    """What this rank's link moves while EVERY rank runs the end-to-end leg's copy pattern for a whole step: ``reps`` copies
+    of ``up_bytes`` host->device and of ``down_bytes`` device->host, back to back on two streams, no kernels.  Returns
+    (seconds, GB/s down, GB/s up).  Short probes overstate a shared host: ranks that finish early free the others' path."""
+    import torch
+
+    h_up = torch.empty(up_bytes, dtype=torch.uint8, pin_memory=True)
+    h_dn = torch.empty(down_bytes, dtype=torch.uint8, pin_memory=True)
+    d_up = torch.empty(up_bytes, dtype=torch.uint8, device=dev)
+    d_dn = torch.empty(down_bytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    with torch.cuda.stream(s1):
+        d_up.copy_(h_up, non_blocking=True)   # first touch
+    with torch.cuda.stream(s2):
+        h_dn.copy_(d_dn, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        with torch.cuda.stream(s1):
+            d_up.copy_(h_up, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_dn.copy_(d_dn, non_blocking=True)
+    s2.synchronize()
+    t_down = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    t_all = time.perf_counter() - t0
+    barrier()
+    del h_up, h_dn, d_up, d_dn
+    torch.cuda.empty_cache()
+    return t_all, reps * down_bytes / t_down / 1e9, reps * up_bytes / t_all / 1e9
+
+
 def verify_one_track(plan, x, res):
     """One track of the bench batch against the oracle at the parity tolerance (outside every timed region)."""
     from oracle import frontend as ofe
@@ -435,12 +467,27 @@ def ours(args, rank, world, local_rank):
         together = pcie_probe(dev) if world > 1 else alone
         barrier()
         pcie = {"alone": alone, "all_ranks_together": together}
-        if world > 1:
-            agg = torch.tensor([together["bidir_each_gbs"]], dtype=torch.float64, device=dev)
-            dist.all_reduce(agg, op=dist.ReduceOp.SUM)
-            pcie["all_ranks_together_sum_each_direction_gbs"] = float(agg.item())
     pipe = engine.HostPipeline(plan, n, 2, chunk, engine.FRONTEND_OUTPUTS)
-    tracks = [host_pool[i % pool_n] for i in range(nt)]
+    nt_e2e, link_rates = nt, None
+    if world > 1 and pcie is not None:
+        # Every rank runs the end-to-end leg's copy pattern for one whole step at once (no kernels): the rate each GPU's
+        # link sustains is what the host gives that GPU, and on this kind of box the GPUs do not share it evenly.  The
+        # end-to-end shards are sized by these rates (sharding.partition(weights=...)), so that all ranks finish
+        # together; the device-resident `value` above keeps equal shards.
+        n_chunks_probe = (nt + chunk - 1) // chunk
+        _, down_gbs, up_gbs = pcie_sustained(dev, chunk * 2 * n * 4, pipe.d2h_bytes_per_chunk, n_chunks_probe, barrier)
+        mine_r = torch.tensor([down_gbs, up_gbs], dtype=torch.float64, device=dev)
+        all_r = [torch.zeros_like(mine_r) for _ in range(world)]
+        dist.all_gather(all_r, mine_r)
+        link_rates = [[float(v) for v in t.tolist()] for t in all_r]
+        down = [r[0] for r in link_rates]
+        pcie["sustained_step_pattern"] = {"down_gbs_per_rank": down, "up_gbs_per_rank": [r[1] for r in link_rates],
+                                          "sum_down_gbs": float(sum(down)), "min_down_gbs": float(min(down))}
+        # whole chunks per rank: a partial last chunk would still copy full-size output buffers back
+        unit = chunk if (nt * world) % chunk == 0 else 1
+        shard = sharding.partition([n * unit] * (nt * world // unit), world, weights=down)[rank]
+        nt_e2e = len(shard) * unit
+    tracks = [host_pool[i % pool_n] for i in range(nt_e2e)]
     sink = []
 
     def consume(ci, first, cnt, host_out):
@@ -461,6 +508,16 @@ def ours(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     s_e2e_max = float(t.item())
     n_chunks = (nt + chunk - 1) // chunk
+    # bytes this rank really moved per step (a partial last chunk still copies whole output buffers), summed over ranks
+    moved = torch.tensor([nt_e2e * 2 * n * 4, ((nt_e2e + chunk - 1) // chunk) * d2h_chunk_full, nt_e2e], dtype=torch.float64, device=dev)
+    per_rank_tracks = [nt_e2e]
+    if world > 1:
+        gathered = [torch.zeros_like(moved) for _ in range(world)]
+        dist.all_gather(gathered, moved)
+        per_rank_tracks = [int(g[2].item()) for g in gathered]
+        moved = torch.stack(gathered).sum(dim=0)
+    e2e_up_total, e2e_down_total = float(moved[0].item()), float(moved[1].item())
+    assert sum(per_rank_tracks) == world * nt, per_rank_tracks
 
     # ---- informational: the byte-reduced pipeline that analyse_track's host stages need -----------------------------
     # (HPSS curves and true peak computed on the device, magnitude and tempogram never downloaded; NOT the contract's
@@ -479,7 +536,7 @@ def ours(args, rank, world, local_rank):
                 pool16 = [torch.from_numpy(np.ascontiguousarray(
                     np.clip(np.round(t.numpy().reshape(2, n) * 32767.0), -32768, 32767).astype(np.int16).T).reshape(-1)).pin_memory()
                     for t in host_pool]
-                src = [pool16[i % pool_n] for i in range(nt)]
+                src = [pool16[i % pool_n] for i in range(nt_e2e)]
             pipe_a = engine.HostPipeline(plan, n, 2, chunk, engine.ANALYSIS_OUTPUTS, pcm16=pcm16)
             pipe_a.run(src, consume)
             barrier()
@@ -563,9 +620,14 @@ def ours(args, rank, world, local_rank):
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                          "algorithmic_bytes_per_launch": k1_bytes},
             "e2e": {"value": world * audio_per_step / s_e2e_max, "unit": UNIT,
-                    "h2d_bytes_per_step": nt * 2 * n * 4, "d2h_bytes_per_step": d2h_full,
+                    "h2d_bytes_per_step": int(e2e_up_total / world), "d2h_bytes_per_step": int(e2e_down_total / world),
                     "steps": e2e_steps, "s_per_step": s_e2e_max, "chunk_tracks": chunk,
-                    "h2d_gbs_per_gpu": nt * 2 * n * 4 / s_e2e_max / 1e9, "d2h_gbs_per_gpu": d2h_full / s_e2e_max / 1e9},
+                    "h2d_gbs_per_gpu": e2e_up_total / world / s_e2e_max / 1e9,
+                    "d2h_gbs_per_gpu": e2e_down_total / world / s_e2e_max / 1e9,
+                    "tracks_per_rank": per_rank_tracks,
+                    "sharding": ("equal shards" if link_rates is None else
+                                 "shards sized by the host-link rate every rank sustains while all ranks copy "
+                                 "(sharding.partition(weights=...)); bytes are the per-GPU average")},
             "gpu_launches": int(launches),
             "verified": (verified or {}).get("ok"),
             "verification": verified,
@@ -575,13 +637,17 @@ def ours(args, rank, world, local_rank):
         if pcie:
             # the busier direction of the end-to-end leg against what the link moves in that direction while both run
             # (all ranks together: the host's ceiling at N > 1)
-            lim = pcie.get("all_ranks_together_sum_each_direction_gbs", pcie["all_ranks_together"]["bidir_each_gbs"])
+            # N = 1: against the short both-directions probe.  N > 1: against what the links sustain, summed over ranks, while
+            # every rank runs the leg's own copy pattern for a whole step (the host's ceiling)
+            sus = pcie.get("sustained_step_pattern")
+            lim = sus["sum_down_gbs"] if sus else pcie["all_ranks_together"]["bidir_each_gbs"]
             busy = world * max(line["e2e"]["h2d_gbs_per_gpu"], line["e2e"]["d2h_gbs_per_gpu"])
             line["e2e"]["pcie"] = pcie
             line["e2e"]["pcie_ceiling_gbs"] = lim
             line["e2e"]["pcie_frac"] = busy / lim if lim else None
             # per-GPU efficiency of the end-to-end leg against one GPU that has the host to itself
-            line["e2e"]["per_gpu_link_share"] = (pcie["all_ranks_together"]["bidir_each_gbs"] / pcie["alone"]["bidir_each_gbs"]
+            share_now = (sus["sum_down_gbs"] / world) if sus else pcie["all_ranks_together"]["bidir_each_gbs"]
+            line["e2e"]["per_gpu_link_share"] = (share_now / pcie["alone"]["bidir_each_gbs"]
                                                  if pcie["alone"] and pcie["alone"]["bidir_each_gbs"] else None)
         if e2e_analysis:
             line["e2e_analysis_outputs"] = e2e_analysis
