@@ -289,36 +289,57 @@ def pcie_probe(dev, nbytes=1 << 30, reps=3):
     return out
 
 
-def pcie_sustained(dev, up_bytes, down_bytes, reps, barrier):
-    """What this rank's link moves while EVERY rank runs the end-to-end leg's copy pattern for a whole step: ``reps`` copies
-    of ``up_bytes`` host->device and of ``down_bytes`` device->host, back to back on two streams, no kernels.  Returns
-    (seconds, GB/s down, GB/s up).  Short probes overstate a shared host: ranks that finish early free the others' path."""
+def pcie_sustained(dev, up_bytes, down_bytes, seconds, barrier):
+    """What this rank's link moves while EVERY rank keeps copying: pieces of ``down_bytes`` device->host and ``up_bytes``
+    host->device (the end-to-end leg's ratio), two of each in flight, until ``seconds`` have passed on every rank; only
+    pieces that completed inside the window count, so no rank is measured on a host the others have already left.
+    (A fixed amount of work per rank overstates a shared host: ranks that finish early free the others' path.)
+    Returns (GB/s down, GB/s up)."""
     import torch
 
     h_up = torch.empty(up_bytes, dtype=torch.uint8, pin_memory=True)
-    h_dn = torch.empty(down_bytes, dtype=torch.uint8, pin_memory=True)
-    d_up = torch.empty(up_bytes, dtype=torch.uint8, device=dev)
+    h_dn = [torch.empty(down_bytes, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    d_up = [torch.empty(up_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
     d_dn = torch.empty(down_bytes, dtype=torch.uint8, device=dev)
     s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    with torch.cuda.stream(s1):
-        d_up.copy_(h_up, non_blocking=True)   # first touch
-    with torch.cuda.stream(s2):
-        h_dn.copy_(d_dn, non_blocking=True)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(reps):
+    for b in range(2):   # first touch
         with torch.cuda.stream(s1):
-            d_up.copy_(h_up, non_blocking=True)
+            d_up[b].copy_(h_up, non_blocking=True)
         with torch.cuda.stream(s2):
-            h_dn.copy_(d_dn, non_blocking=True)
-    s2.synchronize()
-    t_down = time.perf_counter() - t0
+            h_dn[b].copy_(d_dn, non_blocking=True)
+    barrier()
+    ev_dn, ev_up, done_dn, done_up, i = [], [], 0, 0, 0
+    t0 = time.perf_counter()
+    while True:
+        with torch.cuda.stream(s1):
+            d_up[i % 2].copy_(h_up, non_blocking=True)
+            e = torch.cuda.Event()
+            e.record(s1)
+            ev_up.append(e)
+        with torch.cuda.stream(s2):
+            h_dn[i % 2].copy_(d_dn, non_blocking=True)
+            e = torch.cuda.Event()
+            e.record(s2)
+            ev_dn.append(e)
+        i += 1
+        if i >= 2:
+            ev_dn[i - 2].synchronize()   # keep two pieces in flight per direction
+            if time.perf_counter() - t0 >= seconds:
+                done_dn = i - 1
+                done_up = sum(1 for e in ev_up if e.query())
+                break
+    elapsed = time.perf_counter() - t0
+    # keep the link busy until every rank has closed its window, then drain
+    for _ in range(2):
+        with torch.cuda.stream(s1):
+            d_up[0].copy_(h_up, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_dn[0].copy_(d_dn, non_blocking=True)
     torch.cuda.synchronize()
-    t_all = time.perf_counter() - t0
     barrier()
     del h_up, h_dn, d_up, d_dn
     torch.cuda.empty_cache()
-    return t_all, reps * down_bytes / t_down / 1e9, reps * up_bytes / t_all / 1e9
+    return done_dn * down_bytes / elapsed / 1e9, done_up * up_bytes / elapsed / 1e9
 
 
 def verify_one_track(plan, x, res):
@@ -474,8 +495,8 @@ def ours(args, rank, world, local_rank):
         # link sustains is what the host gives that GPU, and on this kind of box the GPUs do not share it evenly.  The
         # end-to-end shards are sized by these rates (sharding.partition(weights=...)), so that all ranks finish
         # together; the device-resident `value` above keeps equal shards.
-        n_chunks_probe = (nt + chunk - 1) // chunk
-        _, down_gbs, up_gbs = pcie_sustained(dev, chunk * 2 * n * 4, pipe.d2h_bytes_per_chunk, n_chunks_probe, barrier)
+        piece = 8   # an eighth of a chunk per copy: ~100 MB down, ~64 MB up
+        down_gbs, up_gbs = pcie_sustained(dev, chunk * 2 * n * 4 // piece, pipe.d2h_bytes_per_chunk // piece, 1.0, barrier)
         mine_r = torch.tensor([down_gbs, up_gbs], dtype=torch.float64, device=dev)
         all_r = [torch.zeros_like(mine_r) for _ in range(world)]
         dist.all_gather(all_r, mine_r)
