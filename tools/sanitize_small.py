@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from track_analyser_b200 import engine, synth
 
 sr = 44_100
-for n_fft, hop, mels in ((2048, 512, 128), (1024, 256, 64), (4096, 256, 256)):
+for n_fft, hop, mels in ((2048, 512, 128), (1024, 256, 64), (4096, 256, 256), (512, 200, 40), (256, 64, 40), (2048, 441, 128)):
     plan = engine.Plan(sr, n_fft, hop, mels, device=0)
     for ch in (1, 2):
         tracks = [synth.synth_track(3 + i, d, sr, ch) for i, d in enumerate((0.51, 1.237, 0.9))]

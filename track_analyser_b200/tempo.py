@@ -4,6 +4,8 @@
 (tempo.py:38) run on the GPU (csrc/stft_fused.cu -> onset.cu -> autocorr.cu);
 the remaining lag masking, peak interpolation, onset regression and grid
 construction (tempo.py:42-75, :78-175) are scalar host logic on those outputs.
+That host half restates the reference's decisions in the reference's order (a bit-exact integer contract leaves no other
+choice); with ``track_analyser_b200.install()`` the reference's own tempo.py runs on the same device outputs instead.
 """
 
 from __future__ import annotations

@@ -6,6 +6,11 @@ Same public names and semantics as /root/reference/src/track_analyser/utils.py:
 (:73-146).  WAV files are decoded by ``io.load_audio``; inputs whose sample rate
 differs from ``target_sr`` are converted on the device by ``resample.resample``
 (the reference's resampy call, utils.py:55-70).
+
+This file is out-of-path glue that SURVEY.md section 8b obliges the package to mirror: ``AudioInput`` has to keep the
+reference's fields and order, and ``coerce_audio`` restates the reference's branches (file / array / AudioInput, mono
+and stereo views) statement by statement so that the callers' behaviour is the same.  It is a transcription of that
+contract, not a design of its own; with ``track_analyser_b200.install()`` the reference's own utils.py is what runs.
 """
 
 from __future__ import annotations
