@@ -268,11 +268,12 @@ _pack_pool = None
 _COPY_PIECE = 2 << 20   # floats per host-to-device copy (8 MB)
 
 
-def upload(plan: Plan, tracks: Sequence[np.ndarray], out: "torch.Tensor | None" = None) -> DeviceBatch:
+def upload(plan: Plan, tracks: Sequence[np.ndarray], out: "torch.Tensor | None" = None, wait: bool = True) -> DeviceBatch:
     """Host tracks -> one flat device buffer (``out`` if it is a float32 tensor on the plan's device that is large enough,
     else a new one).  A track that already sits in pinned memory is copied from where it is; pageable ones go through the
     process-wide pinned staging buffer, filled by a few threads (numpy's copy releases the GIL and one core moves
-    ~12 GB/s, a fifth of what the link takes)."""
+    ~12 GB/s, a fifth of what the link takes).  ``wait=False``: when every track is pinned, return with the copies
+    enqueued on the current stream instead of waiting for them (the staging buffer is not involved then)."""
     global _pack_pool
     tracks = [np.asarray(t, dtype=np.float32) for t in tracks]
     chans = {1 if t.ndim == 1 else t.shape[0] for t in tracks}
@@ -316,7 +317,8 @@ def upload(plan: Plan, tracks: Sequence[np.ndarray], out: "torch.Tensor | None" 
             for a in range(0, n, _COPY_PIECE):
                 b = min(n, a + _COPY_PIECE)
                 dev[off + a: off + b].copy_(src[a:b], non_blocking=True)
-        torch.cuda.current_stream(dev.device).synchronize()
+        if wait or pageable:
+            torch.cuda.current_stream(dev.device).synchronize()
     return DeviceBatch(plan, dev, offsets, n_samples, channels)
 
 

@@ -327,7 +327,7 @@ def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] 
         chunks += [(sr, ch, idxs[c0: c0 + chunk_tracks]) for c0 in range(0, len(idxs), chunk_tracks)]
 
     uploaded: "queue.Queue" = queue.Queue(maxsize=2)
-    # device PCM buffers go round between the two threads (at most four exist: one being filled, two queued, one in use)
+    # device PCM buffers go round between the two threads (at most five exist: two being filled, two queued, one in use)
     # instead of being allocated per chunk: a buffer comes back once the kernels that read it have finished
     pcm_free: "queue.Queue" = queue.Queue()
     pcm_made = [0]
@@ -335,7 +335,7 @@ def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] 
     def pcm_buffer(n_floats: int):
         while True:
             try:
-                buf = pcm_free.get(block=pcm_made[0] >= 4)
+                buf = pcm_free.get(block=pcm_made[0] >= 5)
             except queue.Empty:
                 buf = None
             if buf is not None and buf.numel() >= n_floats:
@@ -347,25 +347,26 @@ def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] 
             return torch.empty(n_floats, dtype=torch.float32, device=f"cuda:{dev_index}")
 
     def uploader():
+        # Two halves per chunk, one chunk apart: `issue` enqueues the PCM copies and the device half of the fingerprints on
+        # this thread's stream and returns; `complete` waits for them, compares and hands the chunk over.  The next chunk's
+        # copies are already enqueued while this one's are being waited for, so the link never idles between chunks.
         try:
             stream = torch.cuda.Stream(dev_index)
             with cf.ThreadPoolExecutor(max_workers=8) as tp, torch.cuda.stream(stream):
-                for sr, ch, idxs in chunks:
-                    _u = [time.perf_counter()]
-                    cand, bad = [], []
+                def issue(sr, ch, idxs):
+                    st = dict(sr=sr, ch=ch, t0=time.perf_counter(), cand=[], bad=[], batch=None, buf=None, host_fp=[], fps=None,
+                              done=None)
                     for i in idxs:
                         c = _batch_buffer(audios[i])
-                        (cand if (c is not None and c[1] == ch and c[0].shape[-1] > 0) else bad).append((i, c))
-                    batch, good = None, []
+                        (st["cand"] if (c is not None and c[1] == ch and c[0].shape[-1] > 0) else st["bad"]).append((i, c))
+                    cand = st["cand"]
                     if cand:
                         plan_a = runtime.get_plan(sr, *_PLAN_A, device=device)
                         # (the host half of the fingerprints runs in the pool while the PCM travels)
-                        host_fp = [tp.submit(_mono_fingerprint, audios[i].samples) for i, _ in cand] if ch == 2 else []
+                        st["host_fp"] = [tp.submit(_mono_fingerprint, audios[i].samples) for i, _ in cand] if ch == 2 else []
                         need = sum((c[0].size + 3) & ~3 for _, c in cand)
-                        buf = pcm_buffer(max(need, 4))
-                        batch = engine.upload(plan_a, [c[0] for _, c in cand], out=buf)
-                        _u.append(time.perf_counter())
-                        ok = [True] * len(cand)
+                        st["buf"] = pcm_buffer(max(need, 4))
+                        batch = st["batch"] = engine.upload(plan_a, [c[0] for _, c in cand], out=st["buf"], wait=False)
                         if ch == 2:
                             # one stereo run may serve the mono stages only if mono == mean(stereo) sample for sample
                             # (utils.py:116): two 64-bit sums over the bit patterns, formed on the device from the stereo PCM
@@ -376,22 +377,43 @@ def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] 
                                 nat.check(plan_a.lib.ta_mono_mix_fingerprint(
                                     C.c_void_p(batch.pcm.data_ptr() + 4 * int(batch.offsets[j])), int(batch.n_samples[j]),
                                     C.c_void_p(fps.data_ptr() + 16 * j), st_ptr))
-                            dev_fp = fps.cpu().numpy().view(np.uint64).reshape(-1, 2)
-                            ok = [tuple(int(v) & 0xffffffff for v in dev_fp[j]) == host_fp[j].result() for j in range(len(cand))]
+                            st["fps"] = torch.empty(2 * len(cand), dtype=torch.int64, pin_memory=True)
+                            st["fps"].copy_(fps, non_blocking=True)
+                        st["done"] = torch.cuda.Event()
+                        st["done"].record()
+                    return st
+
+                def complete(st):
+                    cand, bad, batch, ch = st["cand"], st["bad"], st["batch"], st["ch"]
+                    good = []
+                    if cand:
+                        st["done"].synchronize()
+                        ok = [True] * len(cand)
+                        if ch == 2:
+                            dev_fp = st["fps"].numpy().view(np.uint64).reshape(-1, 2)
+                            ok = [tuple(int(v) & 0xffffffff for v in dev_fp[j]) == st["host_fp"][j].result() for j in range(len(cand))]
                         if not all(ok):   # rare: re-upload only the consistent tracks, the others take the single-track path
                             bad += [ic for ic, o in zip(cand, ok) if not o]
                             cand = [ic for ic, o in zip(cand, ok) if o]
-                            batch = engine.upload(plan_a, [c[0] for _, c in cand], out=buf) if cand else None
+                            plan_a = runtime.get_plan(st["sr"], *_PLAN_A, device=device)
+                            batch = engine.upload(plan_a, [c[0] for _, c in cand], out=st["buf"]) if cand else None
                             if batch is None:
-                                pcm_free.put(buf)
+                                pcm_free.put(st["buf"])
                         good = [(i, c[0]) for i, c in cand]
-                    bad = [i for i, _ in bad]
-                    _u.append(time.perf_counter())
-                    uploaded.put((sr, ch, good, bad, batch))
+                    t1 = time.perf_counter()
+                    uploaded.put((st["sr"], ch, good, [i for i, _ in bad], batch))
                     if trace:
-                        _u.append(time.perf_counter())
-                        print("[ta uploader] upload %.1f, fingerprints %.1f, queue %.1f ms"
-                              % tuple(1e3 * (b - a) for a, b in zip(_u, _u[1:])), file=sys.stderr)
+                        print("[ta uploader] chunk ready %.1f ms after its copies were enqueued, queue %.1f ms"
+                              % (1e3 * (t1 - st["t0"]), 1e3 * (time.perf_counter() - t1)), file=sys.stderr)
+
+                prev = None
+                for sr, ch, idxs in chunks:
+                    cur = issue(sr, ch, idxs)
+                    if prev is not None:
+                        complete(prev)
+                    prev = cur
+                if prev is not None:
+                    complete(prev)
             uploaded.put(None)
         except BaseException as exc:  # noqa: BLE001 - handed to the consuming thread
             uploaded.put(exc)
@@ -416,81 +438,81 @@ def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] 
             results[i] = TrackAnalysisResult(audio=audios[i], stems=None, **stages)
         free_slots.append(slot)
 
-    while True:
-        _t = [time.perf_counter()]
-        item = uploaded.get()
-        if item is None:
-            break
-        if isinstance(item, BaseException):
-            raise item
-        sr, channels, good, bad, batch = item
-        for i in bad:
-            results[i] = analyse_track(audios[i], seed=seed)   # e.g. mono samples that are not the mean of the stereo pair
-        if not good:
-            continue
-        _t.append(time.perf_counter())
-        plan_a = runtime.get_plan(sr, *_PLAN_A, device=device)
-        plan_b = runtime.get_plan(sr, *_PLAN_B, device=device)
-        tracks = [b for _, b in good]
-        outs_a = engine.available_outputs(plan_a, engine.ANALYSIS_OUTPUTS)
-        if not all(t.shape[-1] >= plan_a.meter_block * sr for t in tracks):
-            outs_a = tuple(o for o in outs_a if o not in ("kw_blocks", "lufs"))
-        runs = [((*_PLAN_A, channels), plan_a, batch, outs_a), ((*_PLAN_B, channels), plan_b, batch.rebind(plan_b), ("ltas",))]
-        if channels == 1:
-            # a mono track's stereo stage analyses the duplicated channel pair (stereo.py:42-59): its own small run
-            runs.append(((*_PLAN_A, 2), plan_a, engine.upload(plan_a, [np.vstack([t, t]) for t in tracks]),
-                         ("moments", "band_energy")))
-        launched = []
-        for key, plan, bt, outs in runs:
-            # output buffers are reused by the next chunk of the same geometry (this thread waits for the copies below
-            # before it takes another chunk), which saves ~30 allocations per chunk
-            bkey = (key, bt.n_samples.tobytes(), outs)
-            bufs = buffers.get(bkey)
-            if bufs is None:
-                while len(buffers) >= 3:   # the runs of one chunk; a chunk of another geometry replaces them
-                    buffers.pop(next(iter(buffers)))
-                bufs = buffers[bkey] = engine.FrontendBuffers(bt, outs)
-            engine.run_device(plan, bt, bufs)
-            launched.append((key, plan, bt, bufs))
-        # every requested output array of the batch goes to one slot of the shared-memory ring with one copy each; the
-        # workers cut their track's views out of the mapping instead of receiving pickled arrays
-        specs, cur = {}, 0
-        for key, plan, bt, bufs in launched:
-            arrays = {}
-            for name in bufs.requested:
-                t = bufs.t[name]
-                arrays[name] = (cur, tuple(t.shape), np.dtype(str(t.dtype).replace("torch.", "")).str)
-                cur += (t.numel() * t.element_size() + 63) & ~63
-            specs[key] = (plan.geometry(), bt.geometry(with_cqt="chroma_cqt" in bufs.requested), arrays)
-        if cur > ring.slot_bytes:
-            while pending:   # nobody may be reading the file while it is re-created
-                collect(pending.pop(0))
-            ring.ensure(cur)
-        while not free_slots:
-            collect(pending.pop(0))
-        slot = free_slots.pop(0)
-        base = slot * ring.slot_bytes
-        for key, plan, bt, bufs in launched:
-            for name, (off, shape, dtype) in specs[key][2].items():
-                dst = np.ndarray(shape, dtype=dtype, buffer=ring.mm, offset=base + off)
-                torch.from_numpy(dst).copy_(bufs.t[name], non_blocking=True)
-        main_stream.synchronize()
-        pcm_free.put(batch.pcm._base if batch.pcm._base is not None else batch.pcm)   # the whole buffer, not the slice in use
-        del launched, batch
-        _t.append(time.perf_counter())
-        tasks = []
-        for j, (i, _) in enumerate(good):
-            a = audios[i]
-            meta = dict(sample_rate=a.sample_rate, path=a.path, mono_shape=np.asarray(a.samples).shape,
-                        stereo_shape=None if a.stereo_samples is None else np.asarray(a.stereo_samples).shape)
-            tasks.append((ring.path, base, specs, j, meta, seed))
-        futs = [pool.submit(_stage_worker, t) for t in tasks] if pool is not None else [_stage_worker(t) for t in tasks]
-        pending.append((futs, [i for i, _ in good], slot))
-        _t.append(time.perf_counter())
-        if trace:
-            print("[ta analyse_tracks] chunk of %d: wait for upload %.1f, kernels + copy to shm %.1f, submit %.1f ms"
-                  % ((len(good),) + tuple(1e3 * (b - a) for a, b in zip(_t, _t[1:]))), file=sys.stderr)
     try:
+        while True:
+            _t = [time.perf_counter()]
+            item = uploaded.get()
+            if item is None:
+                break
+            if isinstance(item, BaseException):
+                raise item
+            sr, channels, good, bad, batch = item
+            for i in bad:
+                results[i] = analyse_track(audios[i], seed=seed)   # e.g. mono samples that are not the mean of the stereo pair
+            if not good:
+                continue
+            _t.append(time.perf_counter())
+            plan_a = runtime.get_plan(sr, *_PLAN_A, device=device)
+            plan_b = runtime.get_plan(sr, *_PLAN_B, device=device)
+            tracks = [b for _, b in good]
+            outs_a = engine.available_outputs(plan_a, engine.ANALYSIS_OUTPUTS)
+            if not all(t.shape[-1] >= plan_a.meter_block * sr for t in tracks):
+                outs_a = tuple(o for o in outs_a if o not in ("kw_blocks", "lufs"))
+            runs = [((*_PLAN_A, channels), plan_a, batch, outs_a), ((*_PLAN_B, channels), plan_b, batch.rebind(plan_b), ("ltas",))]
+            if channels == 1:
+                # a mono track's stereo stage analyses the duplicated channel pair (stereo.py:42-59): its own small run
+                runs.append(((*_PLAN_A, 2), plan_a, engine.upload(plan_a, [np.vstack([t, t]) for t in tracks]),
+                             ("moments", "band_energy")))
+            launched = []
+            for key, plan, bt, outs in runs:
+                # output buffers are reused by the next chunk of the same geometry (this thread waits for the copies below
+                # before it takes another chunk), which saves ~30 allocations per chunk
+                bkey = (key, bt.n_samples.tobytes(), outs)
+                bufs = buffers.get(bkey)
+                if bufs is None:
+                    while len(buffers) >= 3:   # the runs of one chunk; a chunk of another geometry replaces them
+                        buffers.pop(next(iter(buffers)))
+                    bufs = buffers[bkey] = engine.FrontendBuffers(bt, outs)
+                engine.run_device(plan, bt, bufs)
+                launched.append((key, plan, bt, bufs))
+            # every requested output array of the batch goes to one slot of the shared-memory ring with one copy each; the
+            # workers cut their track's views out of the mapping instead of receiving pickled arrays
+            specs, cur = {}, 0
+            for key, plan, bt, bufs in launched:
+                arrays = {}
+                for name in bufs.requested:
+                    t = bufs.t[name]
+                    arrays[name] = (cur, tuple(t.shape), np.dtype(str(t.dtype).replace("torch.", "")).str)
+                    cur += (t.numel() * t.element_size() + 63) & ~63
+                specs[key] = (plan.geometry(), bt.geometry(with_cqt="chroma_cqt" in bufs.requested), arrays)
+            if cur > ring.slot_bytes:
+                while pending:   # nobody may be reading the file while it is re-created
+                    collect(pending.pop(0))
+                ring.ensure(cur)
+            while not free_slots:
+                collect(pending.pop(0))
+            slot = free_slots.pop(0)
+            base = slot * ring.slot_bytes
+            for key, plan, bt, bufs in launched:
+                for name, (off, shape, dtype) in specs[key][2].items():
+                    dst = np.ndarray(shape, dtype=dtype, buffer=ring.mm, offset=base + off)
+                    torch.from_numpy(dst).copy_(bufs.t[name], non_blocking=True)
+            main_stream.synchronize()
+            pcm_free.put(batch.pcm._base if batch.pcm._base is not None else batch.pcm)   # the whole buffer, not the slice in use
+            del launched, batch
+            _t.append(time.perf_counter())
+            tasks = []
+            for j, (i, _) in enumerate(good):
+                a = audios[i]
+                meta = dict(sample_rate=a.sample_rate, path=a.path, mono_shape=np.asarray(a.samples).shape,
+                            stereo_shape=None if a.stereo_samples is None else np.asarray(a.stereo_samples).shape)
+                tasks.append((ring.path, base, specs, j, meta, seed))
+            futs = [pool.submit(_stage_worker, t) for t in tasks] if pool is not None else [_stage_worker(t) for t in tasks]
+            pending.append((futs, [i for i, _ in good], slot))
+            _t.append(time.perf_counter())
+            if trace:
+                print("[ta analyse_tracks] chunk of %d: wait for upload %.1f, kernels + copy to shm %.1f, submit %.1f ms"
+                      % ((len(good),) + tuple(1e3 * (b - a) for a, b in zip(_t, _t[1:]))), file=sys.stderr)
         for entry in pending:
             collect(entry)
         th.join()
