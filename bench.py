@@ -586,17 +586,22 @@ def ours(args, rank, world, local_rank):
             pool_audio.append(AudioInput(samples=np.mean(st, axis=0), sample_rate=SR, stereo_samples=st))
         na = min(args.analysis_tracks, nt)
         srcs = [pool_audio[i % pool_n] for i in range(na)]
-        pipeline.analyse_tracks(srcs[: min(na, 2 * args.chunk_tracks)], chunk_tracks=args.chunk_tracks)   # forks the workers, warms the plans
-        barrier()
-        t0 = time.perf_counter()
-        out = pipeline.analyse_tracks(srcs, chunk_tracks=args.chunk_tracks)
-        dt = time.perf_counter() - t0
-        ta = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
-        assert len(out) == na and all(90.0 <= o.beat.bpm <= 135.0 for o in out)
-        e2e_track = {"value": world * na * args.seconds / float(ta.item()), "unit": UNIT, "tracks_per_gpu": na,
-                     "s_total": float(ta.item()), "host_workers": pipeline._worker_count(None),
+        # warm-up: forks the workers, builds the plans, and runs enough chunks for the device PCM buffers that go round
+        # between uploader and kernel thread (five) to exist before the timed call
+        pipeline.analyse_tracks(srcs[: min(na, 6 * args.chunk_tracks)], chunk_tracks=args.chunk_tracks)
+        runs_s = []
+        for _ in range(2):   # host-side scheduling of ~15 processes on 16 cores varies from run to run: both times are reported
+            barrier()
+            t0 = time.perf_counter()
+            out = pipeline.analyse_tracks(srcs, chunk_tracks=args.chunk_tracks)
+            ta = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+            runs_s.append(float(ta.item()))
+            assert len(out) == na and all(90.0 <= o.beat.bpm <= 135.0 for o in out)
+        s_mean = float(np.mean(runs_s))
+        e2e_track = {"value": world * na * args.seconds / s_mean, "unit": UNIT, "tracks_per_gpu": na,
+                     "s_total": s_mean, "s_runs": runs_s, "host_workers": pipeline._worker_count(None),
                      "note": "pipeline.analyse_tracks: host AudioInput in -> TrackAnalysisResult dataclasses out (beats, structure, "
                              "loudness, harmony incl. chroma_cqt, features, stereo); host stages in worker processes"}
 

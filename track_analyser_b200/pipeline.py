@@ -352,6 +352,10 @@ def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] 
         # copies are already enqueued while this one's are being waited for, so the link never idles between chunks.
         try:
             stream = torch.cuda.Stream(dev_index)
+            # pinned landing places of the device fingerprints, one per chunk in flight (allocated once: a pinned allocation
+            # per chunk costs milliseconds and synchronises with the device)
+            fp_host = [torch.empty(2 * max(1, chunk_tracks), dtype=torch.int64, pin_memory=True) for _ in range(3)]
+            issued = [0]
             with cf.ThreadPoolExecutor(max_workers=8) as tp, torch.cuda.stream(stream):
                 def issue(sr, ch, idxs):
                     st = dict(sr=sr, ch=ch, t0=time.perf_counter(), cand=[], bad=[], batch=None, buf=None, host_fp=[], fps=None,
@@ -377,7 +381,8 @@ def analyse_tracks(sources, *, seed: int = DEFAULT_SEED, workers: Optional[int] 
                                 nat.check(plan_a.lib.ta_mono_mix_fingerprint(
                                     C.c_void_p(batch.pcm.data_ptr() + 4 * int(batch.offsets[j])), int(batch.n_samples[j]),
                                     C.c_void_p(fps.data_ptr() + 16 * j), st_ptr))
-                            st["fps"] = torch.empty(2 * len(cand), dtype=torch.int64, pin_memory=True)
+                            st["fps"] = fp_host[issued[0] % 3][: 2 * len(cand)]
+                            issued[0] += 1
                             st["fps"].copy_(fps, non_blocking=True)
                         st["done"] = torch.cuda.Event()
                         st["done"].record()
