@@ -176,3 +176,23 @@ def test_unsupported_configurations_fail_loudly():
         engine.analyse_batch(p, [np.zeros(44_100, np.float32)], ("chroma_cqt",))
     with pytest.raises(ValueError):
         harmony.key_estimate(np.zeros(8000, np.float32), 8_000)
+
+
+def test_full_size_properties_of_the_round_two_outputs():
+    """3-minute 44.1 kHz stereo track (BASELINE configs[1]): properties that need no oracle.  A power-of-two gain is exact in
+    binary floating point, so the inf-normalised constant-Q chroma, its tuning estimate and the roll-off bins must not move
+    by a single bit; a track's results must not depend on its neighbours in the batch."""
+    sr = 44_100
+    x = synth.synth_track(synth.DEFAULT_SEED, 180.0, sr, 2)
+    plan = plan_for(sr)
+    outs = ("chroma_cqt", "cqt_tuning", "rolloff_bin", "self_similarity", "chroma", "tuning")
+    r1 = engine.analyse_batch(plan, [x], outs)[0]
+    assert r1["chroma_cqt"].shape == (12, 15_504) and np.all(np.isfinite(r1["chroma_cqt"]))
+    assert float(np.max(r1["chroma_cqt"])) == 1.0 and float(np.min(r1["chroma_cqt"])) >= 0.0
+    r2 = engine.analyse_batch(plan, [0.5 * x], outs)[0]
+    for k in ("chroma_cqt", "cqt_tuning", "rolloff_bin", "chroma", "tuning"):
+        np.testing.assert_array_equal(np.asarray(r2[k]), np.asarray(r1[k]), err_msg=k)
+    other = synth.synth_track(91, 47.0, sr, 2)
+    rb = engine.analyse_batch(plan, [other, x, other[:, :30_000]], outs)[1]
+    for k in outs:
+        np.testing.assert_array_equal(np.asarray(rb[k]), np.asarray(r1[k]), err_msg=k)
