@@ -887,3 +887,36 @@ def test_self_similarity_novelty_on_the_device():
         ref = host(olr.mfcc(olr.power_to_db(np.asarray(mel, dtype=float) + 1e-9)), context)
         np.testing.assert_allclose(r["self_similarity"], ref, rtol=RTOL, atol=1e-7)
     assert np.all(res[2]["self_similarity"] == 0.0)   # 3 s < two context windows: the reference leaves the curve at zero
+
+
+def test_tensor_core_projection_variant_runs_and_is_tf32_accurate():
+    """The tcgen05.mma (kind::tf32) form of the chroma contraction, kept as the measured alternative to the CUDA-core kernel
+    (profiles/r2_row_g_tensor_core_evidence.md; TA_PROJECT is read once per process, hence the subprocesses).  It must
+    run on ragged batches and agree with the product kernel to TF32 accuracy -- which is also why it is not the product path."""
+    import subprocess
+    import sys
+    import tempfile
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r)\n"
+        "from track_analyser_b200 import engine, synth\n"
+        "plan = engine.Plan(44100, 2048, 512, 128, device=0)\n"
+        "tracks = [synth.synth_track(5 + i, d, 44100, 2) for i, d in enumerate((31.0, 2.7, 12.3, 0.4))]\n"
+        "res = engine.analyse_batch(plan, tracks, ('chroma',))\n"
+        "np.savez(sys.argv[1], *[np.asarray(r['chroma']) for r in res])\n" % root)
+    outs = {}
+    with tempfile.TemporaryDirectory() as tmp:
+        for mode in ("tma", "umma"):
+            path = os.path.join(tmp, mode + ".npz")
+            env = dict(os.environ, TA_PROJECT=mode)
+            p = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True, timeout=600, env=env)
+            assert p.returncode == 0, p.stderr[-2000:]
+            with np.load(path) as z:
+                outs[mode] = [z[k] for k in z.files]
+    for a, b in zip(outs["tma"], outs["umma"]):
+        assert a.shape == b.shape and np.all(np.isfinite(b))
+        assert float(np.max(np.abs(a - b))) < 4e-3          # TF32: 10 mantissa bits per operand
+        assert float(np.max(b)) == pytest.approx(1.0, abs=1e-6)
+    big = np.abs(outs["tma"][0] - outs["umma"][0])
+    assert float(np.mean(big <= ATOL + RTOL * np.abs(outs["tma"][0]))) < 0.9   # ... and that is not the parity tolerance

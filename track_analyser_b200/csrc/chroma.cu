@@ -461,6 +461,165 @@ __global__ void __launch_bounds__(CP_THREADS, 2) chroma_project_tma_kernel(const
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// A/B variant for the north star's "tensor-core filterbank projection, kept only if ncu shows it wins" clause
+// (profiles/r2_row_g_tensor_core_evidence.md): the same contraction chroma[c, t] = sum_k fb[k, c] * |X[k, t]|^2 issued as
+// tcgen05.mma kind::tf32 with the accumulator in tensor memory.  Selected by TA_PROJECT=umma for chroma-only requests; it
+// is NOT the product path: one TF32 pass keeps 10 mantissa bits of every operand, which does not meet the rtol 1e-4 parity
+// bar (a parity-grade version needs two more passes over residual tiles that CUDA cores would have to produce).
+//   D[128 frames, 16] (TMEM, fp32)  +=  A[128 frames, 8 bins] (smem, MN-major, 128-byte swizzle)  x  B[8 bins, 16] (smem, K-major)
+// A CTA owns 128 frames of one track.  Per stage, TMA brings four boxes of {32 frames, 64 bins} with the 128-byte swizzle
+// the UMMA descriptor names (one box = eight 1 KB atoms of 8 bins x 32 frames); 128 threads square the stage in
+// place (the projection runs on the power spectrum), and one thread issues eight MMAs and commits them to the stage's
+// "empty" mbarrier, behind which the next TMA loads are issued.  Epilogue: tcgen05.ld, inf-norm, store.
+static constexpr size_t SMEM_OPTIN_LIMIT = 232448;   // 227 KB per CTA on sm_100
+static constexpr int UM_FRAMES = 128, UM_KCH = 64, UM_STAGES = 4, UM_N = 16;
+static constexpr int UM_TILES = 8;   // 128-frame tiles per CTA
+static constexpr int UM_CONSUMERS = 256, UM_THREADS = UM_CONSUMERS + 32;   // eight warps square the stages, one feeds the TMA unit
+static constexpr int UM_STAGE_BYTES = UM_FRAMES * UM_KCH * 4;   // 32 KB
+
+__device__ __forceinline__ unsigned long long umma_desc(unsigned smem_addr, unsigned lbo_bytes, unsigned sbo_bytes, unsigned layout) {
+    // cute::UMMA::SmemDescriptor: start >> 4 in [0,14), LBO >> 4 in [16,30), SBO >> 4 in [32,46), version 1 in [46,48), layout in [61,64)
+    return (unsigned long long)((smem_addr >> 4) & 0x3fff) | ((unsigned long long)((lbo_bytes >> 4) & 0x3fff) << 16) |
+           ((unsigned long long)((sbo_bytes >> 4) & 0x3fff) << 32) | (1ull << 46) | ((unsigned long long)layout << 61);
+}
+
+__global__ void __launch_bounds__(UM_THREADS, 1) chroma_project_umma_kernel(const TrackDesc* __restrict__ tracks,
+                                                                     const CUtensorMap* __restrict__ maps,
+                                                                     const float* __restrict__ fb, float* __restrict__ out, int n_bins) {
+    extern __shared__ __align__(1024) unsigned char usm[];
+    const TrackDesc td = tracks[blockIdx.y];
+    const int tile0 = blockIdx.x * UM_TILES, n_tiles_track = (td.n_frames + UM_FRAMES - 1) / UM_FRAMES;
+    if (tile0 >= n_tiles_track) return;
+    const int n_tiles = min(UM_TILES, n_tiles_track - tile0);   // this CTA's run of 128-frame tiles (one filterbank staging)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_chunks = (n_bins + UM_KCH - 1) / UM_KCH, k_pad = n_chunks * UM_KCH;
+    const unsigned base = (static_cast<unsigned>(__cvta_generic_to_shared(usm)) + 1023u) & ~1023u;   // 1 KB atoms
+    unsigned char* gen = usm + (base - static_cast<unsigned>(__cvta_generic_to_shared(usm)));
+    float* bsm = reinterpret_cast<float*>(gen + UM_STAGES * UM_STAGE_BYTES);       // [k_pad / 4][2][8][4]
+    const unsigned b_base = base + UM_STAGES * UM_STAGE_BYTES;
+    const unsigned bar0 = b_base + k_pad * UM_N * 4;   // full[UM_STAGES], empty[UM_STAGES], done, then the TMEM address slot
+    unsigned* slot = reinterpret_cast<unsigned*>(gen + UM_STAGES * UM_STAGE_BYTES + size_t(k_pad) * UM_N * 4 + (2 * UM_STAGES + 1) * 8);
+    const unsigned long long map = reinterpret_cast<unsigned long long>(maps + blockIdx.y);
+    auto full = [&](int s) { return bar0 + 8 * s; };
+    auto empty = [&](int s) { return bar0 + 8 * (UM_STAGES + s); };
+    const unsigned done = bar0 + 8 * 2 * UM_STAGES;
+    if (tid == 0) {
+        for (int s = 0; s < 2 * UM_STAGES + 1; ++s)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0 + 8 * s) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) {   // 32 columns of tensor memory for the 128 x 16 fp32 accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(slot))) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    // B: the track's filterbank, K-major core matrices of 8 (chroma) x 4 (bins) floats, two per 4-bin group (chroma 0-7, 8-15)
+    const float* __restrict__ w = fb + size_t(blockIdx.y) * n_bins * 12;
+    for (int i = tid; i < k_pad * UM_N; i += UM_THREADS) {
+        const int kk = i / UM_N, n = i % UM_N;
+        bsm[(kk >> 2) * 64 + (n >> 3) * 32 + (n & 7) * 4 + (kk & 3)] = (n < 12 && kk < n_bins) ? w[kk * 12 + n] : 0.f;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const unsigned tmem = *slot;
+    const int total = n_tiles * n_chunks;   // stages are numbered through the CTA's whole run: g = tile * n_chunks + chunk
+    if (warp == UM_CONSUMERS / 32) {   // producer warp: one thread keeps UM_STAGES loads in flight and never joins the consumers' barriers
+        if (lane == 0)
+            for (int g = 0; g < total; ++g) {
+                const int st = g % UM_STAGES, f0 = (tile0 + g / n_chunks) * UM_FRAMES, chunk = g % n_chunks;
+                if (g >= UM_STAGES) mbar_wait(empty(st), ((g / UM_STAGES) - 1) & 1);   // the MMAs that read the stage are done
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(full(st)), "r"(UM_STAGE_BYTES) : "memory");
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                                 ::"r"(base + st * UM_STAGE_BYTES + q * (UM_STAGE_BYTES / 4)), "l"(map), "r"(f0 + 32 * q),
+                                   "r"(chunk * UM_KCH), "r"(full(st)) : "memory");
+            }
+        return;
+    }
+    // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B tf32, A MN-major, B K-major, N = 16, M = 128
+    constexpr unsigned idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((UM_N >> 3) << 17) | ((128u >> 4) << 24);
+    for (int g = 0; g < total; ++g) {
+        const int st = g % UM_STAGES, c = g % n_chunks, ti = g / n_chunks;
+        mbar_wait(full(st), (g / UM_STAGES) & 1);
+        float4* tile = reinterpret_cast<float4*>(gen + st * UM_STAGE_BYTES);
+#pragma unroll 4
+        for (int i = tid; i < UM_STAGE_BYTES / 16; i += UM_CONSUMERS) {   // |X| -> |X|^2 in place (element-wise: the swizzle does not matter)
+            float4 v = tile[i];
+            v.x *= v.x; v.y *= v.y; v.z *= v.z; v.w *= v.w;
+            tile[i] = v;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 1, %0;" ::"n"(UM_CONSUMERS) : "memory");   // also: the previous tile's tcgen05.ld are behind this
+        if (tid == 0) {
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < UM_KCH / 8; ++j) {
+                // MN-major 32-bit operands: 128-byte swizzle with 32-byte atoms (cute::UMMA::LayoutType::SWIZZLE_128B_BASE32B = 1,
+                // the layout CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes; with the 16-byte-atom swizzle the MMA returns zeros),
+                // K atoms of 4 rows (512 B): an 8-bin MMA spans two of them (SBO), the 32-frame boxes are the M atoms (LBO)
+                const unsigned long long ad = umma_desc(base + st * UM_STAGE_BYTES + j * 1024, UM_STAGE_BYTES / 4, 512, 1);
+                const unsigned long long bd = umma_desc(b_base + (c * (UM_KCH / 8) + j) * 512, 256, 128, 0);
+                const unsigned acc = (c | j) ? 1u : 0u;   // the first MMA of a tile overwrites the accumulator
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+                             ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(acc), "r"(0u) : "memory");
+            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(empty(st)) : "memory");
+            if (c == n_chunks - 1)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(done) : "memory");
+        }
+        if (c == n_chunks - 1 && warp < 4) {   // tile finished: warp w reads TMEM lanes 32 w .. 32 w + 31, one frame per thread
+            mbar_wait(done, ti & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            unsigned r[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                         : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                         : "r"(tmem + ((unsigned(warp) * 32u) << 16)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int t = (tile0 + ti) * UM_FRAMES + warp * 32 + lane;
+            if (t < td.n_frames) {
+                float mx = 0.f;
+#pragma unroll
+                for (int q = 0; q < 12; ++q) mx = fmaxf(mx, fabsf(__uint_as_float(r[q])));
+                const float l0 = (mx < 1.1754943508222875e-38f) ? 1.0f : mx;
+                float* dst = out + size_t(td.pitch_off) * 12 + t;
+#pragma unroll
+                for (int q = 0; q < 12; ++q) dst[size_t(q) * td.ld] = __uint_as_float(r[q]) / l0;
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(UM_CONSUMERS) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem) : "memory");
+}
+
+// tensor maps for the variant above: boxes of {32 frames, 64 bins}, 128-byte swizzle
+static int build_magnitude_maps_umma(const ta_plan* plan, const HostBatch& hb, const float* mag, void* d_maps, cudaStream_t stream) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return TA_ERR_UNSUPPORTED;
+    std::vector<CUtensorMap> maps(hb.n_tracks);
+    const int B = plan->n_bins;
+    for (int i = 0; i < hb.n_tracks; ++i) {
+        const TrackDesc& t = hb.tracks[i];
+        const cuuint64_t dims[2] = {cuuint64_t(t.n_frames), cuuint64_t(B)};
+        const cuuint64_t strides[1] = {cuuint64_t(t.ld) * sizeof(float)};
+        const cuuint32_t box[2] = {32, UM_KCH};
+        const cuuint32_t estr[2] = {1, 1};
+        const CUresult r = enc(&maps[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(mag) + size_t(t.pitch_off) * B, dims,
+                               strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return TA_ERR_UNSUPPORTED;
+    }
+    TA_CUDA(cudaMemcpyAsync(d_maps, maps.data(), sizeof(CUtensorMap) * hb.n_tracks, cudaMemcpyHostToDevice, stream));
+    return TA_OK;
+}
+
 // workspace layout helpers ----------------------------------------------------------------
 static void pip_range(const ta_plan* plan, int& kmin, int& kmax) {
     const double sr = plan->desc.sample_rate, fmax = std::min(4000.0, sr / 2.0), fmin = 150.0;
@@ -572,6 +731,19 @@ static int launch_project(const ta_plan* plan, const HostBatch& hb, const TrackD
         return TA_ERR_INVALID;
     }
     static const bool use_tma = [] { const char* e = std::getenv("TA_PROJECT"); return !(e && e[0] == 'l'); }();  // TA_PROJECT=ldg
+    static const bool use_umma = [] { const char* e = std::getenv("TA_PROJECT"); return e && e[0] == 'u'; }();    // TA_PROJECT=umma (A/B)
+    if (use_umma && CHROMA && !ROLL && d_maps) {
+        const int n_chunks = (plan->n_bins + UM_KCH - 1) / UM_KCH;
+        const size_t smem = 1024 + size_t(UM_STAGES) * UM_STAGE_BYTES + size_t(n_chunks) * UM_KCH * UM_N * 4 + (2 * UM_STAGES + 2) * 8;
+        if (smem <= SMEM_OPTIN_LIMIT && build_magnitude_maps_umma(plan, hb, mag, d_maps, stream) == TA_OK) {
+            TA_CUDA(cudaFuncSetAttribute(chroma_project_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            chroma_project_umma_kernel<<<dim3((hb.max_frames + UM_FRAMES * UM_TILES - 1) / (UM_FRAMES * UM_TILES), hb.n_tracks), UM_THREADS, smem, stream>>>(
+                d_tracks, reinterpret_cast<const CUtensorMap*>(d_maps), fb, chroma, plan->n_bins);
+            count_launch();
+            TA_CUDA(cudaGetLastError());
+            return TA_OK;
+        }
+    }
     const size_t tma_smem = size_t(TP_STAGES) * TP_STAGE_FLOATS * 4 + (CHROMA ? size_t(plan->n_bins) * 12 * sizeof(float) : 0) +
                             TP_STAGES * 8 + 128;
     if (use_tma && d_maps && tma_smem <= 113 * 1024 && build_magnitude_maps(plan, hb, mag, d_maps, stream) == TA_OK) {
