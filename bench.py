@@ -623,6 +623,21 @@ def ours(args, rank, world, local_rank):
                 traffic = tj["traffic_bytes"]
         except Exception:
             pass
+        # what else bounds K1: pipe utilisations of the same launch from the committed ncu --set full capture
+        # (profiles/r2_k1_ncu_summary.txt); the HBM fraction above is the contract's figure, these say why it is what it is
+        other_pipes = None
+        try:
+            import re
+
+            txt = open(os.path.join(ROOT, "profiles", "r2_k1_ncu_summary.txt")).read()
+            if args.tracks_per_gpu == 128 and args.seconds == 180.0:
+                pick = lambda key: float(re.search(key + r"=([0-9.eE+-]+)", txt).group(1))  # noqa: E731
+                other_pipes = {"fp32_fma_pipe_pct": pick("fma%"), "issue_slots_pct": pick("issue%"), "lsu_pipe_pct": pick("lsu%"),
+                               "dram_pct": pick("dram%"), "occupancy_pct": pick("occ%"),
+                               "shared_memory_bytes_per_16_frame_tile": 1.4e6, "shared_memory_floor_cycles_per_tile": 11000,
+                               "cycles_per_tile": 27700, "source": "profiles/r2_k1_ncu_summary.txt, profiles/r2_notes.md"}
+        except Exception:
+            pass
         # algorithmic bytes of the other stages, per launch of this batch
         stage_bytes = {
             "stft_mel_features": k1_bytes,
@@ -644,7 +659,7 @@ def ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "kernel": "stft_fused_kernel<2048,16,stereo,4>", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
-                         "algorithmic_bytes_per_launch": k1_bytes},
+                         "algorithmic_bytes_per_launch": k1_bytes, "other_pipes": other_pipes},
             "e2e": {"value": world * audio_per_step / s_e2e_max, "unit": UNIT,
                     "h2d_bytes_per_step": int(e2e_up_total / world), "d2h_bytes_per_step": int(e2e_down_total / world),
                     "steps": e2e_steps, "s_per_step": s_e2e_max, "chunk_tracks": chunk,
